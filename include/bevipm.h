@@ -1,0 +1,122 @@
+/*
+ * bevipm.h -- C ABI of the B200 (sm_100a) multi-view IPM warp + BEV fusion library.
+ *
+ * The reference (sea-sky-web/Vision-based-Spatio-Temporal-Analysis) is pure Python and has no
+ * native boundary of its own; the interface this ABI stands behind is the pair of torch modules
+ *
+ *   GeometryTransformer.forward(feats, intrinsics, extrinsics, img_size) -> [B,V,C,Hb,Wb]
+ *       /root/reference/project/models/fusion/geometry.py:80-163   (grid_sample branch :142-162)
+ *   SimpleFusion.forward / ConcatFusion.forward (bev_maps) -> [B,C,Hb,Wb] / [B,V*C,Hb,Wb]
+ *       /root/reference/project/models/fusion/fusion.py:11-22, :39-46
+ *
+ * called back to back from BEVNet.forward (models/model_wrapper.py:68-69).  Each entry point
+ * below names the reference lines it replaces.  The Python binding a maintainer adds is the
+ * ctypes stub in INTEGRATION.md (bevipm/_lib.py is that stub, shipped).
+ *
+ * Conventions
+ *   - plain C types only; every pointer is caller-owned; the library never allocates, frees or
+ *     retains device memory (bevipm_warp_fuse_host is the one exception: it keeps a per-thread
+ *     device staging arena, released by bevipm_host_release).
+ *   - device entry points are stream-ordered on `stream` (a cudaStream_t passed as void*); they
+ *     never synchronise the device.
+ *   - return value: 0 on success, negative bevipm_status on failure; bevipm_last_error() gives
+ *     the thread-local message.  Nothing throws across this boundary.
+ *   - all strides are in ELEMENTS of the tensor's dtype.
+ */
+#ifndef BEVIPM_H_
+#define BEVIPM_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEVIPM_VERSION 100 /* 0.1.0 */
+
+enum bevipm_status {
+    BEVIPM_OK = 0,
+    BEVIPM_ERR_BAD_ARG = -1,     /* null pointer, non-positive extent, unknown enum */
+    BEVIPM_ERR_UNSUPPORTED = -2, /* legal request this build has no kernel for */
+    BEVIPM_ERR_CUDA = -3         /* a CUDA runtime call failed; message has cudaGetErrorString */
+};
+
+enum bevipm_dtype { BEVIPM_F32 = 0, BEVIPM_BF16 = 1 };
+
+/* View-axis reduction.  SUM/MEAN/MAX = SimpleFusion modes (fusion.py:17-22; MEAN divides by V,
+ * MAX competes against the zeros of out-of-view cells).  NONE writes the per-view maps
+ * [B,V,C,Hb,Wb], i.e. GeometryTransformer's own output, which ConcatFusion merely reshapes. */
+enum bevipm_mode { BEVIPM_SUM = 0, BEVIPM_MEAN = 1, BEVIPM_MAX = 2, BEVIPM_NONE = 3 };
+
+typedef struct bevipm_desc {
+    int32_t B, V, C;        /* frames, views (cameras), channels */
+    int32_t Hf, Wf;         /* feature-map size */
+    int32_t Hb, Wb;         /* BEV grid size */
+    int32_t img_h, img_w;   /* the img_size argument of GeometryTransformer.forward (geometry.py:83) */
+    int32_t mode;           /* bevipm_mode */
+    int32_t in_dtype;       /* bevipm_dtype of feats (fwd) / grad_feats is always f32 (bwd) */
+    int32_t out_dtype;      /* bevipm_dtype of out (fwd) / grad_out (bwd) */
+    int32_t variant;        /* 0 = library picks the kernel; >0 forces one, for sweeps */
+    int32_t reserved;
+    int64_t fs_b, fs_v, fs_c, fs_y, fs_x; /* feats[b,v,c,y,x] strides; fs_c == 1 is the NHWC fast path */
+    int64_t os_b, os_v, os_c, os_y, os_x; /* out[b,(v,)c,i,j] strides; os_v is read only for NONE */
+} bevipm_desc;
+
+int bevipm_version(void);
+const char *bevipm_last_error(void);
+
+/* Number of kernels this library has launched in the calling process (all threads). */
+int64_t bevipm_launch_count(void);
+
+/*
+ * Fused forward: replaces geometry.py:120-162 (homography, projection of every BEV cell centre,
+ * bilinear zero-padded sampling) and fusion.py:17-22 in ONE launch, without materialising the
+ * per-view maps.
+ *   feats  device, dtype in_dtype, logical [B,V,C,Hf,Wf] with strides fs_*
+ *   K      device f32 [B*V*9]   row-major 3x3 intrinsics           (geometry.py:35-40)
+ *   Rt34   device f32 [B*V*12]  row-major [R|t], world -> camera   (geometry.py:41-52)
+ *   xs, ys device f32 [Wb], [Hb] cell-centre world coordinates, torch.linspace values (geometry.py:26-27)
+ *   out    device, dtype out_dtype, [B,C,Hb,Wb] (or [B,V,C,Hb,Wb] for NONE) with strides os_*
+ */
+int bevipm_warp_fuse_fwd(const bevipm_desc *d, const void *feats, const float *K, const float *Rt34,
+                         const float *xs, const float *ys, void *out, void *stream);
+
+/*
+ * Backward w.r.t. the features (autograd of geometry.py:161 + fusion.py:18-21, reached from
+ * train.py:243).  grad_feats is f32 with strides fs_*, must be zero-filled by the caller and
+ * is accumulated into with atomics.  MAX is not differentiable here (BEVIPM_ERR_UNSUPPORTED).
+ */
+int bevipm_warp_fuse_bwd(const bevipm_desc *d, const void *grad_out, const float *K, const float *Rt34,
+                         const float *xs, const float *ys, float *grad_feats, void *stream);
+
+/* Sample positions only: ix, iy device f32 [B,V,Hb,Wb] in feature pixels (geometry.py:144-158 plus
+ * grid_sample's un-normalisation).  Used by tests and by the algorithmic-byte counter. */
+int bevipm_sample_coords(const bevipm_desc *d, const float *K, const float *Rt34, const float *xs,
+                         const float *ys, float *ix, float *iy, void *stream);
+
+/* Layout pre-pass for callers that hold the encoder's NCHW-contiguous output (cnn_encoder.py:65-70):
+ * src [N,C,H,W] -> dst [N,H,W,C], same dtype (bevipm_dtype). */
+int bevipm_nchw_to_nhwc(const void *src, void *dst, int32_t N, int32_t C, int32_t H, int32_t W,
+                        int32_t dtype, void *stream);
+
+/* SimpleFusion on already materialised per-view maps (fusion.py:17-22): in [B,V,inner] contiguous
+ * -> out [B,inner], inner = C*Hb*Wb.  mode = SUM / MEAN / MAX.  (The fused forward above never
+ * needs this; it exists so the stand-alone SimpleFusion module also runs on our kernels.) */
+int bevipm_fuse_views(const void *in, void *out, int64_t B, int32_t V, int64_t inner, int32_t mode,
+                      int32_t in_dtype, int32_t out_dtype, void *stream);
+
+/*
+ * Host-buffer entry (the call a non-torch integrator makes, and what bench.py's e2e times):
+ * feats/out are HOST pointers (pinned for full PCIe rate) laid out as feats [B,V,Hf,Wf,C] and
+ * out [B,Hb,Wb,C] ([B,V,Hb,Wb,C] for NONE); K, Rt34, xs, ys are host arrays.  Frames are streamed
+ * H2D -> kernel -> D2H through a double-buffered device arena and the call returns after the
+ * last byte of `out` has landed.  d's stride fields are ignored.
+ */
+int bevipm_warp_fuse_host(const bevipm_desc *d, const void *feats, const float *K, const float *Rt34,
+                          const float *xs, const float *ys, void *out);
+void bevipm_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVIPM_H_ */

@@ -1,0 +1,336 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the reference's goldens.
+
+fp32: bit-exact (numeric equality, NaN positions equal) -- tolerance 0, well inside the <= 1e-5
+the north star allows.  bf16 features: the fp32 result is bit-exact against the oracle fed the
+up-cast features (what CUDA autocast does for grid_sampler); a bf16 OUTPUT is that result rounded
+to nearest-even, so the bound vs fp32 is one bf16 rounding, 2^-8 relative (<= 1e-2).
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES
+from oracle import ipm_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _same(a: np.ndarray, b: np.ndarray) -> bool:
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(a[~na], b[~nb])
+
+
+def _bcast(z):
+    feats = z["feats"]
+    B, V = feats.shape[:2]
+    K = np.ascontiguousarray(np.broadcast_to(z["K"], (B, V) + z["K"].shape[-2:]))
+    Rt = np.ascontiguousarray(np.broadcast_to(z["Rt"], (B, V) + z["Rt"].shape[-2:]))
+    return feats, K, Rt
+
+
+def _dev_inputs(feats, K, Rt, xs, ys, channels_last, dtype=torch.float32):
+    from bevipm import modules
+    f = torch.from_numpy(np.ascontiguousarray(feats)).to(DEV).to(dtype)
+    if channels_last:
+        f = f.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    B, V = f.shape[:2]
+    Kd, Rd = modules.pack_calibration(torch.from_numpy(K), torch.from_numpy(Rt), B, V, torch.device(DEV))
+    return f, Kd, Rd, torch.from_numpy(np.asarray(xs, np.float32)).to(DEV), torch.from_numpy(np.asarray(ys, np.float32)).to(DEV)
+
+
+def _run(feats, K, Rt, xs, ys, img_size, mode, channels_last, dtype=torch.float32, out_bf16=False, variant=0):
+    from bevipm import _lib, ops
+    f, Kd, Rd, xd, yd = _dev_inputs(feats, K, Rt, xs, ys, channels_last, dtype)
+    out = ops.warp_fuse(f, Kd, Rd, xd, yd, int(img_size[0]), int(img_size[1]), _lib.MODES[mode], out_bf16, variant)
+    torch.cuda.synchronize()
+    return out
+
+
+def _rig_case(B, V, C, fhw, bhw, seed=0):
+    from bevipm import rig
+    K, Rt = rig.look_at_rig(V, seed)
+    K = np.ascontiguousarray(np.broadcast_to(K.numpy(), (B, V, 3, 3)))
+    Rt = np.ascontiguousarray(np.broadcast_to(Rt.numpy(), (B, V, 4, 4)))
+    feats = torch.randn(B, V, C, *fhw, generator=torch.Generator().manual_seed(seed)).numpy()
+    xs, ys = rig.ground_axes(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS)
+    return feats, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE
+
+
+# ---- golden vectors of the reference module ------------------------------------------------------
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+@pytest.mark.parametrize("mode", ["none", "sum", "mean", "max"])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_golden_fp32(golden, case, mode, channels_last):
+    z = golden(case)
+    feats, K, Rt = _bcast(z)
+    out = _run(feats, K, Rt, z["xs"], z["ys"], z["img_size"], mode, channels_last).cpu().numpy()
+    # the oracle is pinned to these goldens bit-for-bit (tests/test_oracle.py); sum/mean goldens carry
+    # ATen's vector-tail reordering, so the fused modes are compared with the oracle's sequential order
+    want = z["out_none"] if mode == "none" else orc.warp_fuse(feats, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]), mode)
+    assert _same(out, want)
+    if mode == "max":
+        assert _same(out, z["out_max"])
+
+
+@pytest.mark.parametrize("case", ["rig_small", "seven_views_3x4", "degenerate", "w_guard"])
+@pytest.mark.parametrize("mode", ["sum", "mean", "none"])
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_golden_backward(golden, case, mode, channels_last):
+    from bevipm import _lib, ops
+    z = golden(case)
+    feats, K, Rt = _bcast(z)
+    f, Kd, Rd, xd, yd = _dev_inputs(feats, K, Rt, z["xs"], z["ys"], channels_last)
+    f.requires_grad_(True)
+    out = ops.warp_fuse(f, Kd, Rd, xd, yd, int(z["img_size"][0]), int(z["img_size"][1]), _lib.MODES[mode], False, 0)
+    cot = torch.from_numpy(z["cotangent_none"] if mode == "none" else z["cotangent"]).to(DEV)
+    (out * cot).sum().backward()
+    got = f.grad.cpu().numpy()
+    ref = z["grad_" + mode]
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()   # atomics: order differs, tolerance 1e-5 rel
+
+
+# ---- every fused-kernel variant against the oracle, ragged shapes --------------------------------
+
+@pytest.mark.parametrize("variant", list(range(1, 11)))
+@pytest.mark.parametrize("mode", ["mean", "sum"])
+def test_variants_fp32_ragged(variant, mode):
+    # Hb, Wb not multiples of any patch; C = 136 leaves a partial channel chunk
+    feats, K, Rt, xs, ys, img = _rig_case(2, 5, 136, (31, 53), (37, 91), seed=2)
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, mode)
+    out = _run(feats, K, Rt, xs, ys, img, mode, True, variant=variant).cpu().numpy()
+    assert _same(out, want)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 7, 8, 9, 10])
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_variants_bf16_ragged(variant, out_bf16):
+    feats, K, Rt, xs, ys, img = _rig_case(2, 5, 264, (31, 53), (37, 91), seed=4)
+    fb = torch.from_numpy(feats).bfloat16()
+    want = torch.from_numpy(orc.warp_fuse(fb.float().numpy(), K, Rt, xs, ys, img, "mean"))
+    out = _run(fb.float().numpy(), K, Rt, xs, ys, img, "mean", True, dtype=torch.bfloat16, out_bf16=out_bf16,
+               variant=variant).cpu()
+    if out_bf16:
+        assert out.dtype == torch.bfloat16
+        assert torch.equal(out, want.bfloat16())
+        rel = (out.float() - want).abs().max() / want.abs().max()
+        assert rel <= 1e-2
+    else:
+        assert _same(out.numpy(), want.numpy())
+
+
+@pytest.mark.parametrize("mode", ["max", "none"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_max_and_per_view_fast_path(mode, dtype):
+    feats, K, Rt, xs, ys, img = _rig_case(1, 7, 72, (34, 60), (30, 90), seed=6)
+    f = torch.from_numpy(feats).to(dtype).float().numpy()
+    want = orc.warp_fuse(f, K, Rt, xs, ys, img, mode)
+    out = _run(f, K, Rt, xs, ys, img, mode, True, dtype=dtype).cpu().numpy()
+    assert _same(out, want)
+
+
+def test_strided_kernel_nchw_bf16():
+    feats, K, Rt, xs, ys, img = _rig_case(1, 3, 7, (20, 33), (19, 45), seed=8)
+    f = torch.from_numpy(feats).bfloat16().float().numpy()
+    want = orc.warp_fuse(f, K, Rt, xs, ys, img, "mean")
+    out = _run(f, K, Rt, xs, ys, img, "mean", False, dtype=torch.bfloat16).cpu().numpy()
+    assert _same(out, want)
+
+
+# ---- BASELINE.json shapes at full size ----------------------------------------------------------------
+
+@pytest.mark.parametrize("name", ["c1", "c3"])
+def test_full_size_fp32_vs_oracle(name):
+    from bevipm import rig
+    wl = rig.WORKLOADS[name]
+    feats, K, Rt, xs, ys, img = _rig_case(1, wl.views, wl.channels, wl.feat_hw, wl.bev_hw, seed=0)
+    nhwc = np.ascontiguousarray(feats.transpose(0, 1, 3, 4, 2)).transpose(0, 1, 4, 2, 3)
+    want = orc.warp_fuse(nhwc, K, Rt, xs, ys, img, "mean", channels_last_out=True)
+    out = _run(feats, K, Rt, xs, ys, img, "mean", True).cpu().numpy()
+    assert _same(out, want)
+    assert np.count_nonzero(out) > 0.5 * out.size
+
+
+def test_full_size_c2_bf16_frames_and_properties():
+    """BASELINE config 1 (the bench workload): 8 frames x 7 views x 1024 ch bf16.  One frame is checked
+    against the oracle; the whole batch through size-independent properties."""
+    from bevipm import _lib, ops, rig
+    wl = rig.WORKLOADS["c2"]
+    B, V, C = wl.frames, wl.views, wl.channels
+    g = torch.Generator(device=DEV).manual_seed(0)
+    f = torch.randn(B, V, *wl.feat_hw, C, device=DEV, generator=g).bfloat16().permute(0, 1, 4, 2, 3)
+    K, Rt = rig.look_at_rig(V, 0)
+    Kd = K[None].expand(B, -1, -1, -1).contiguous().to(DEV)
+    Rd = Rt[None, :, :3, :].expand(B, -1, -1, -1).contiguous().to(DEV)
+    xs, ys = rig.ground_axes(*wl.bev_hw, wl.bounds)
+    xd, yd = xs.to(DEV), ys.to(DEV)
+    img = wl.img_size
+    run = lambda t, mode="mean", obf=False: ops.warp_fuse(t, Kd, Rd, xd, yd, img[0], img[1], _lib.MODES[mode], obf, 0)
+    out = run(f)
+    assert out.shape == (B, C, *wl.bev_hw) and out.dtype == torch.float32
+    # (1) frame 3 against the oracle, bit-exact
+    f3 = f[3:4].float().cpu().numpy()
+    want = orc.warp_fuse(f3, K[None].numpy(), Rt[None].numpy(), xs.numpy(), ys.numpy(), img, "mean")
+    assert _same(out[3:4].cpu().numpy(), want)
+    # (2) bf16 output is the rounding of the fp32 output
+    assert torch.equal(run(f, obf=True), out.bfloat16())
+    # (3) mean == sum / V exactly (IEEE division of the same accumulator)
+    s = run(f, "sum")
+    assert torch.equal(out, s / torch.tensor(float(V), device=DEV))   # tensor divisor: IEEE division
+    # (4) homogeneity: scaling the features by 2 scales the BEV by 2 exactly (power of two)
+    assert torch.equal(run(f * 2), out * 2)
+    # (5) frames are independent: permuting frames permutes the output
+    perm = torch.tensor([5, 0, 7, 2, 1, 6, 3, 4], device=DEV)
+    assert torch.equal(run(f[perm]), out[perm])
+    # (6) all-ones features: every cell = (in-bounds tap weight summed over views) / V, identical across channels
+    ones = torch.ones_like(f[:1])
+    cov = run(ones)
+    assert torch.equal(cov[:, :1].expand_as(cov), cov)
+    assert float(cov.max()) <= 1.0 + 1e-6 and float(cov.min()) >= 0.0
+    # (7) fused mean == our per-view maps reduced sequentially
+    pv = run(f[:1], "none")
+    acc = pv[:, 0].clone()
+    for v in range(1, V):
+        acc += pv[:, v]
+    assert torch.equal(out[:1], acc / torch.tensor(float(V), device=DEV))
+
+
+# ---- properties with known answers ----------------------------------------------------------------------
+
+def test_ramp_features_return_coordinates():
+    """feature = x (resp. y) ramp  =>  output = ix (resp. iy) wherever all four taps are in bounds."""
+    from bevipm import _lib, ops, rig
+    V, Hf, Wf, Hb, Wb = 3, 40, 64, 36, 100
+    K, Rt = rig.look_at_rig(V, 1)
+    xs, ys = rig.ground_axes(Hb, Wb, rig.WILDTRACK_BOUNDS)
+    ramp = torch.zeros(1, V, 4, Hf, Wf)
+    ramp[:, :, 0] = torch.arange(Wf, dtype=torch.float32)[None, :]
+    ramp[:, :, 1] = torch.arange(Hf, dtype=torch.float32)[:, None]
+    ramp[:, :, 2] = 1.0
+    f = ramp.to(DEV).permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)
+    Kd, Rd = K[None].contiguous().to(DEV), Rt[None, :, :3].contiguous().to(DEV)
+    pv = ops.warp_fuse(f, Kd, Rd, xs.to(DEV), ys.to(DEV), 1080, 1920, _lib.NONE, False, 0)
+    ix, iy = ops.sample_coords(Kd, Rd, xs.to(DEV), ys.to(DEV), (Hf, Wf), (1080, 1920))
+    inside = (ix >= 0) & (ix <= Wf - 1) & (iy >= 0) & (iy <= Hf - 1)
+    assert inside.any()
+    assert torch.allclose(pv[:, :, 0][inside], ix[inside], atol=2e-4)
+    assert torch.allclose(pv[:, :, 1][inside], iy[inside], atol=2e-4)
+    assert torch.allclose(pv[:, :, 2][inside], torch.ones_like(ix[inside]), atol=1e-6)
+    outside = (ix < -1) | (ix > Wf) | (iy < -1) | (iy > Hf)
+    assert outside.any() and float(pv[:, :, 2][outside].abs().max()) == 0.0
+
+
+def test_sample_coords_match_oracle():
+    from bevipm import ops, rig
+    K, Rt = rig.look_at_rig(7, 0)
+    xs, ys = rig.ground_axes(120, 360, rig.WILDTRACK_BOUNDS)
+    ix, iy = ops.sample_coords(K[None].contiguous().to(DEV), Rt[None, :, :3].contiguous().to(DEV), xs.to(DEV), ys.to(DEV),
+                               (135, 240), (1080, 1920))
+    ox, oy = orc.coords(K[None].numpy(), Rt[None].numpy(), xs.numpy(), ys.numpy(), (135, 240), (1080, 1920))
+    assert np.array_equal(ix.cpu().numpy(), ox) and np.array_equal(iy.cpu().numpy(), oy)
+
+
+def test_view_permutation_sum():
+    feats, K, Rt, xs, ys, img = _rig_case(1, 7, 16, (34, 60), (30, 90), seed=9)
+    a = _run(feats, K, Rt, xs, ys, img, "sum", True).cpu().numpy()
+    p = np.array([3, 0, 6, 1, 5, 2, 4])
+    b = _run(feats[:, p], K[:, p], Rt[:, p], xs, ys, img, "sum", True).cpu().numpy()
+    assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max()       # fp32 re-association only
+    m1 = _run(feats, K, Rt, xs, ys, img, "max", True).cpu().numpy()
+    m2 = _run(feats[:, p], K[:, p], Rt[:, p], xs, ys, img, "max", True).cpu().numpy()
+    assert np.array_equal(m1, m2)                                # max is order-free
+
+
+# ---- module surface (the drop-in boundary) ---------------------------------------------------------------
+
+def test_modules_match_reference_golden_and_calibration_forms(golden):
+    import bevipm
+    z = golden("rig_small")
+    feats = torch.from_numpy(z["feats"]).to(DEV)
+    K, Rt = torch.from_numpy(z["K"]).to(DEV), torch.from_numpy(z["Rt"]).to(DEV)
+    B, V = feats.shape[:2]
+    bounds = tuple(float(x) for x in z["bounds"])
+    bev_h, bev_w = (int(x) for x in z["bev_hw"])
+    img = tuple(int(x) for x in z["img_size"])
+    geom = bevipm.GeometryTransformer(bev_h, bev_w, bounds, warp_impl="kornia").to(DEV)
+    assert list(geom.state_dict().keys()) == [] and list(geom.parameters()) == []
+    pv = geom(feats, K, Rt, img_size=img)
+    assert pv.dtype == torch.float32 and _same(pv.cpu().numpy(), z["out_none"])
+    # nested lists (what the loader hands over, wildtrack_loader.py:389-401)
+    pv2 = geom(feats, [[K[b, v] for v in range(V)] for b in range(B)], [[Rt[b, v] for v in range(V)] for b in range(B)], img_size=img)
+    assert torch.equal(pv, pv2)
+    assert _same(bevipm.ConcatFusion()(pv).cpu().numpy(), z["out_concat"])
+    for mode in ("sum", "mean", "max"):
+        want = orc.warp_fuse(z["feats"], z["K"], z["Rt"], z["xs"], z["ys"], img, mode)
+        assert _same(bevipm.SimpleFusion(mode)(pv).cpu().numpy(), want)
+        fused = bevipm.FusedIPM(bev_h, bev_w, bounds, fusion=mode).to(DEV)
+        assert _same(fused(feats, K, Rt, img_size=img).cpu().numpy(), want)
+    cat = bevipm.FusedIPM(bev_h, bev_w, bounds, fusion="concat").to(DEV)(feats, K, Rt, img_size=img)
+    assert _same(cat.cpu().numpy(), z["out_concat"])
+    # shared calibration forms: [V,3,3]/[V,4,4] and a single 2-D pair (geometry.py:100-103)
+    a = geom(feats, K[0], Rt[0], img_size=img)
+    b = geom(feats, K[0][None].expand(B, -1, -1, -1), Rt[0][None].expand(B, -1, -1, -1), img_size=img)
+    assert torch.equal(a, b)
+    c = geom(feats, K[0, 0], Rt[0, 0], img_size=img)
+    d = geom(feats, K[0, 0].expand(B, V, -1, -1), Rt[0, 0].expand(B, V, -1, -1), img_size=img)
+    assert torch.equal(c, d)
+    # fp16 features behave like grid_sampler under autocast: fp32 compute, fp32 result
+    h = geom(feats.half(), K, Rt, img_size=img)
+    assert h.dtype == torch.float32
+
+
+def test_cpu_tensors_are_rejected():
+    import bevipm
+    geom = bevipm.FusedIPM(8, 8, (-1.0, 1.0, -1.0, 1.0))
+    with pytest.raises(RuntimeError):
+        geom(torch.zeros(1, 1, 4, 4, 4), torch.eye(3), torch.eye(4))
+
+
+def test_autograd_through_fused_module_nchw_input():
+    import bevipm
+    feats, K, Rt, xs, ys, img = _rig_case(1, 3, 8, (20, 33), (19, 45), seed=11)
+    f = torch.from_numpy(feats).to(DEV).requires_grad_(True)
+    mod = bevipm.FusedIPM(19, 45, bevipm.rig.WILDTRACK_BOUNDS, fusion="mean").to(DEV)
+    out = mod(f, torch.from_numpy(K).to(DEV), torch.from_numpy(Rt).to(DEV), img_size=img)
+    cot = torch.randn(out.shape, device=DEV, generator=torch.Generator(device=DEV).manual_seed(0))
+    (out * cot).sum().backward()
+    want = orc.warp_fuse_bwd(cot.cpu().numpy(), K, Rt, xs, ys, feats.shape, img, "mean")
+    assert f.grad is not None and f.grad.shape == f.shape
+    assert np.abs(f.grad.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
+
+
+def test_layout_prepass_and_view_reduction_kernels():
+    from bevipm import ops
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for dt in (torch.float32, torch.bfloat16):
+        x = torch.randn(2, 3, 37, 19, 23, device=DEV, generator=g).to(dt)
+        y = ops.to_channels_last5(x)
+        assert y.stride(2) == 1 and torch.equal(x, y)
+    pv = torch.randn(2, 5, 6, 11, 13, device=DEV, generator=g)
+    seq = pv[:, 0].clone()
+    for v in range(1, 5):
+        seq = seq + pv[:, v]
+    assert torch.equal(ops.fuse_views(pv, "sum"), seq)
+    assert torch.equal(ops.fuse_views(pv, "mean"), seq / torch.tensor(5.0, device=DEV))
+    assert torch.equal(ops.fuse_views(pv, "max"), pv.max(dim=1).values)
+
+
+def test_host_buffer_entry_matches_oracle():
+    from bevipm import ops
+    feats, K, Rt, xs, ys, img = _rig_case(3, 4, 32, (27, 48), (24, 72), seed=13)
+    host = torch.from_numpy(np.ascontiguousarray(feats.transpose(0, 1, 3, 4, 2))).pin_memory()
+    out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                             torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")
+    assert _same(out.numpy().transpose(0, 3, 1, 2), want)
+
+
+def test_library_was_the_thing_that_ran():
+    from bevipm import _lib
+    before = _lib.launch_count()
+    feats, K, Rt, xs, ys, img = _rig_case(1, 2, 8, (12, 16), (10, 20), seed=1)
+    _run(feats, K, Rt, xs, ys, img, "mean", True)
+    assert _lib.launch_count() == before + 1

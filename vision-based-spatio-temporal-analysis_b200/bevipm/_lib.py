@@ -1,0 +1,73 @@
+"""ctypes binding of include/bevipm.h -- the stub INTEGRATION.md shows, shipped.
+
+There is no fallback: if libbevipm.so is missing or was built without CUDA the import of the
+product path fails with the reason and the build command.
+"""
+from __future__ import annotations
+
+import ctypes
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "libbevipm.so"
+
+F32, BF16 = 0, 1
+SUM, MEAN, MAX, NONE = 0, 1, 2, 3
+MODES = {"sum": SUM, "mean": MEAN, "max": MAX, "none": NONE, "concat": NONE}
+
+
+class Desc(ctypes.Structure):
+    """struct bevipm_desc (include/bevipm.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in
+                ("B", "V", "C", "Hf", "Wf", "Hb", "Wb", "img_h", "img_w", "mode", "in_dtype", "out_dtype",
+                 "variant", "reserved")] + \
+               [(n, ctypes.c_int64) for n in
+                ("fs_b", "fs_v", "fs_c", "fs_y", "fs_x", "os_b", "os_v", "os_c", "os_y", "os_x")]
+
+
+EXPORTS = (
+    "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
+    "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
+    "bevipm_warp_fuse_host", "bevipm_host_release",
+)
+
+_lib = None
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(
+            f"{LIB_PATH} is missing: the CUDA library is the only implementation of this path. "
+            "Build it with `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc).")
+    L = ctypes.CDLL(str(LIB_PATH))
+    vp, fp, dp = ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Desc)
+    L.bevipm_version.restype = ctypes.c_int
+    L.bevipm_last_error.restype = ctypes.c_char_p
+    L.bevipm_launch_count.restype = ctypes.c_int64
+    L.bevipm_warp_fuse_fwd.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp]
+    L.bevipm_warp_fuse_bwd.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp]
+    L.bevipm_sample_coords.argtypes = [dp, fp, fp, fp, fp, fp, fp, vp]
+    L.bevipm_nchw_to_nhwc.argtypes = [vp, vp, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_int32, vp]
+    L.bevipm_fuse_views.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
+                                    ctypes.c_int32, ctypes.c_int32, vp]
+    L.bevipm_warp_fuse_host.argtypes = [dp, vp, fp, fp, fp, fp, vp]
+    L.bevipm_host_release.restype = None
+    for name in ("bevipm_warp_fuse_fwd", "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc",
+                 "bevipm_fuse_views", "bevipm_warp_fuse_host"):
+        getattr(L, name).restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().bevipm_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"bevipm error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load().bevipm_launch_count())

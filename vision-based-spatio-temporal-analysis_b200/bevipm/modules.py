@@ -1,0 +1,236 @@
+"""Host-side mirror of the reference's projection / fusion modules, over the CUDA library.
+
+Same class names, constructor arguments, forward signatures and error behaviour as
+/root/reference/project/models/fusion/geometry.py and fusion.py, so BEVNet
+(model_wrapper.py:42-43, :68-69) takes them unchanged:
+
+    model.geom   = bevipm.GeometryTransformer(bev_h, bev_w, bounds, warp_impl)   # per-view maps
+    model.fusion = bevipm.ConcatFusion()                                         # as wired today
+or, fused (no [B,V,C,Hb,Wb] tensor ever exists):
+    model.geom   = bevipm.FusedIPM(bev_h, bev_w, bounds, fusion="mean")
+    model.fusion = torch.nn.Identity()
+
+No parameters and no persistent buffers are added (state_dict keys unchanged, geometry.py:21).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+
+def _as_rt34(Rt: torch.Tensor) -> torch.Tensor:
+    """geometry.py:41-59: 4x4 / 3x4 -> [R|t]; 3x3 -> [R|0]; anything else -> [I|0]."""
+    if Rt.dim() == 2:
+        if tuple(Rt.shape) == (4, 4):
+            return Rt[:3, :]
+        if tuple(Rt.shape) == (3, 4):
+            return Rt
+        if tuple(Rt.shape) == (3, 3):
+            return torch.cat([Rt, Rt.new_zeros(3, 1)], dim=1)
+    return torch.eye(3, 4, device=Rt.device if isinstance(Rt, torch.Tensor) else None)
+
+
+def _as_k33(K: torch.Tensor) -> torch.Tensor:
+    """geometry.py:35-40: top-left 3x3, or diag(1000, 1000, 1) when K is not at least 3x3."""
+    if K.dim() != 2 or K.shape[0] < 3 or K.shape[1] < 3:
+        k = torch.eye(3, device=K.device)
+        k[0, 0] = k[1, 1] = 1000.0
+        return k
+    return K[:3, :3]
+
+
+def _select(x, b: int, v: int, V: int, is_k: bool):
+    """get_K / get_Rt of geometry.py:96-118."""
+    if isinstance(x, torch.Tensor):
+        if x.dim() == 4:
+            return x[b, v]
+        if x.dim() == 3:
+            return x[v] if x.shape[0] == V else x[b]
+        if x.dim() == 2:
+            return x[:3, :3] if is_k else x[:4, :4]
+        return torch.eye(3 if is_k else 4)
+    return torch.as_tensor(x[b][v])
+
+
+def pack_calibration(intrinsics, extrinsics, B: int, V: int, device) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Every calibration form GeometryTransformer.forward accepts (geometry.py:96-118) ->
+    dense float32 K [B,V,3,3] and Rt34 [B,V,3,4] on `device`."""
+    def fast(x, tails):
+        return isinstance(x, torch.Tensor) and x.dim() == 4 and tuple(x.shape[:2]) == (B, V) and tuple(x.shape[2:]) in tails
+
+    if fast(intrinsics, {(3, 3)}):
+        K = intrinsics
+    else:
+        K = torch.stack([torch.stack([_as_k33(_select(intrinsics, b, v, V, True)).to(device) for v in range(V)])
+                         for b in range(B)])
+    if fast(extrinsics, {(4, 4), (3, 4)}):
+        Rt = extrinsics[..., :3, :]
+    else:
+        Rt = torch.stack([torch.stack([_as_rt34(_select(extrinsics, b, v, V, False)).to(device) for v in range(V)])
+                          for b in range(B)])
+    K = K.to(device=device, dtype=torch.float32).contiguous()
+    Rt = Rt.to(device=device, dtype=torch.float32).contiguous()
+    return K, Rt
+
+
+class _IPMBase(nn.Module):
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple):
+        super().__init__()
+        self.bev_h = bev_h
+        self.bev_w = bev_w
+        self.bounds = bev_bounds  # (x_min, x_max, y_min, y_max)
+        self.res_x = (bev_bounds[1] - bev_bounds[0]) / bev_w
+        self.res_y = (bev_bounds[3] - bev_bounds[2]) / bev_h
+        self.register_buffer("ground_grid", self._create_ground_grid(), persistent=False)
+        self._axes = {}
+
+    def _create_ground_grid(self) -> torch.Tensor:
+        # geometry.py:24-31 -- the linspace values themselves are part of the contract (rig.ground_axes)
+        min_x, max_x, min_y, max_y = self.bounds
+        xs = torch.linspace(min_x + 0.5 * self.res_x, max_x - 0.5 * self.res_x, self.bev_w)
+        ys = torch.linspace(min_y + 0.5 * self.res_y, max_y - 0.5 * self.res_y, self.bev_h)
+        yy, xx = torch.meshgrid(ys, xs, indexing="ij")
+        return torch.stack([xx, yy, torch.ones_like(xx)], dim=-1)
+
+    def _ground_axes(self, device):
+        key = str(device)
+        if key not in self._axes:
+            g = self.ground_grid
+            self._axes[key] = (g[0, :, 0].to(device=device, dtype=torch.float32).contiguous(),
+                               g[:, 0, 1].to(device=device, dtype=torch.float32).contiguous())
+        return self._axes[key]
+
+    def _run(self, feats, intrinsics, extrinsics, img_size, mode: int, out_bf16: bool, variant: int, layout: str):
+        if feats.dim() != 5:
+            raise ValueError("feats must be [B,V,C,Hf,Wf]")
+        if not feats.is_cuda:
+            raise RuntimeError("bevipm runs on CUDA tensors only: there is no CPU implementation of this path")
+        B, V = feats.shape[:2]
+        if feats.dtype == torch.float16:
+            feats = feats.float()  # grid_sampler's autocast policy is fp32 (the reference under train.py:239)
+        K, Rt = pack_calibration(intrinsics, extrinsics, B, V, feats.device)
+        xs, ys = self._ground_axes(feats.device)
+        if layout == "channels_last" or (layout == "auto" and feats.shape[2] % (4 if feats.dtype == torch.float32 else 8) == 0):
+            feats = ops.to_channels_last5(feats)
+        H_img, W_img = img_size
+        return ops.warp_fuse(feats, K, Rt, xs, ys, int(H_img), int(W_img), mode, out_bf16, variant)
+
+
+class GeometryTransformer(_IPMBase):
+    """Per-view IPM warp, drop-in for geometry.py:12-163 (grid_sample semantics)."""
+
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, warp_impl: str = "grid_sample", layout: str = "keep"):
+        super().__init__(bev_h, bev_w, bev_bounds)
+        # geometry.py:20 -- both names are accepted; 'kornia' executes the grid_sample branch in any
+        # environment without kornia (this image), which is the behaviour mirrored here
+        self.warp_impl = warp_impl if warp_impl in ("grid_sample", "kornia") else "grid_sample"
+        self.layout = layout
+        self._grid_cache = {}
+
+    @staticmethod
+    def _compute_homography(K: torch.Tensor, Rt: torch.Tensor) -> torch.Tensor:
+        """H = K [r1 r2 t] (geometry.py:33-64); tiny host-side helper, called by BEVNet's unused loss."""
+        K = _as_k33(K)
+        Rt34 = _as_rt34(Rt).to(K.device)
+        G = torch.cat([Rt34[:, 0:1], Rt34[:, 1:2], Rt34[:, 3:4]], dim=1)
+        return K @ G
+
+    @staticmethod
+    def _compute_img_to_world_homography(K: torch.Tensor, Rt: torch.Tensor) -> torch.Tensor:
+        """inverse with pinv fallback (geometry.py:66-78)."""
+        H = GeometryTransformer._compute_homography(K, Rt)
+        try:
+            det = torch.det(H)
+        except Exception:
+            det = torch.tensor(float("nan"), device=H.device)
+        if torch.isnan(det) or torch.isinf(det) or det.abs().item() < 1e-8:
+            return torch.linalg.pinv(H)
+        try:
+            return torch.linalg.inv(H)
+        except Exception:
+            return torch.linalg.pinv(H)
+
+    def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
+                img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
+        """feats [B,V,C,Hf,Wf] -> [B,V,C,Hb,Wb] float32 (geometry.py:94: fp32 whatever the input)."""
+        return self._run(feats, intrinsics, extrinsics, img_size, _lib.NONE, False, 0, self.layout)
+
+
+class FusedIPM(_IPMBase):
+    """forward(features, calibration) -> BEV [B,C,Hb,Wb]: GeometryTransformer + SimpleFusion in one
+    kernel launch (geometry.py:80-163 followed by fusion.py:17-22), or ConcatFusion's
+    [B,V*C,Hb,Wb] for fusion='concat'."""
+
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, fusion: str = "mean",
+                 warp_impl: str = "grid_sample", out_dtype: torch.dtype = torch.float32,
+                 layout: str = "auto", variant: int = 0):
+        super().__init__(bev_h, bev_w, bev_bounds)
+        assert fusion in ("sum", "mean", "max", "concat", "none")
+        assert out_dtype in (torch.float32, torch.bfloat16)
+        assert layout in ("auto", "keep", "channels_last")
+        self.fusion = fusion
+        self.warp_impl = warp_impl if warp_impl in ("grid_sample", "kornia") else "grid_sample"
+        self.out_dtype = out_dtype
+        self.layout = layout   # "auto": NCHW-contiguous features go through our transpose pre-pass
+        self.variant = variant
+
+    def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
+                img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
+        out = self._run(feats, intrinsics, extrinsics, img_size, _lib.MODES[self.fusion],
+                        self.out_dtype == torch.bfloat16, self.variant, self.layout)
+        if self.fusion == "concat":
+            B, V, C, Hb, Wb = out.shape
+            return out.reshape(B, V * C, Hb, Wb)   # fusion.py:45-46, channel index v*C + c
+        return out
+
+
+class FusionModule(nn.Module):
+    def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
+        """bev_maps: Tensor[B, V, C, H, W] -> Tensor[B, C, H, W]   (fusion.py:5-8)"""
+        raise NotImplementedError
+
+
+class SimpleFusion(FusionModule):
+    """fusion.py:11-22 on materialised per-view maps (our reduction kernel; mean divides by V)."""
+
+    def __init__(self, mode: str = "sum"):
+        super().__init__()
+        assert mode in ("sum", "mean", "max")
+        self.mode = mode
+
+    def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
+        if bev_maps.requires_grad and torch.is_grad_enabled():
+            # the stand-alone reduction has no hand-written backward; autograd users take the fused module
+            if self.mode == "sum":
+                return bev_maps.sum(dim=1)
+            if self.mode == "mean":
+                return bev_maps.mean(dim=1)
+            return bev_maps.max(dim=1).values
+        return ops.fuse_views(bev_maps, self.mode)
+
+
+class AttentionFusion(FusionModule):
+    """fusion.py:25-36: the reference's placeholder (announces itself once, returns the mean)."""
+
+    def __init__(self):
+        super().__init__()
+        self._warned = False
+        self._mean = SimpleFusion("mean")
+
+    def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
+        if not self._warned:
+            print("[AttentionFusion] Placeholder only. Not implemented.")
+            self._warned = True
+        return self._mean(bev_maps)
+
+
+class ConcatFusion(FusionModule):
+    """fusion.py:39-46: [B,V,C,H,W] -> [B,V*C,H,W], view-major channels."""
+
+    def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
+        B, V, C, H, W = bev_maps.shape
+        return bev_maps.reshape(B, V * C, H, W)

@@ -1,0 +1,241 @@
+"""`bevipm::warp_fuse` -- thin PyTorch custom op over the C ABI (include/bevipm.h).
+
+torch supplies device memory, the current stream and autograd bookkeeping; every FLOP and byte
+of the path runs in libbevipm.so.  CUDA tensors only: the op is registered for device type
+"cuda" and nothing else, so CPU tensors raise instead of silently taking another route.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import Desc, MODES
+
+_DT = {torch.float32: _lib.F32, torch.bfloat16: _lib.BF16}
+
+
+def _stream_ptr(dev) -> int:
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _fill_desc(feat_shape, feat_strides, out_strides, bev_hw, img_hw, mode, in_dt, out_dt, variant) -> Desc:
+    B, V, C, Hf, Wf = feat_shape
+    d = Desc()
+    d.B, d.V, d.C, d.Hf, d.Wf = B, V, C, Hf, Wf
+    d.Hb, d.Wb = bev_hw
+    d.img_h, d.img_w = img_hw
+    d.mode, d.in_dtype, d.out_dtype, d.variant = mode, in_dt, out_dt, variant
+    d.fs_b, d.fs_v, d.fs_c, d.fs_y, d.fs_x = feat_strides
+    d.os_b, d.os_v, d.os_c, d.os_y, d.os_x = out_strides
+    return d
+
+
+def _out_strides5(out: torch.Tensor, per_view: bool):
+    s = out.stride()
+    return tuple(s) if per_view else (s[0], 0, s[1], s[2], s[3])
+
+
+def _is_channels_last5(t: torch.Tensor) -> bool:
+    return t.stride(2) == 1 or t.shape[2] == 1
+
+
+def _alloc_out(feats: torch.Tensor, Hb: int, Wb: int, per_view: bool, dtype, channels_last: bool):
+    B, V, C = feats.shape[:3]
+    if channels_last:
+        if per_view:
+            return torch.empty((B, V, Hb, Wb, C), device=feats.device, dtype=dtype).permute(0, 1, 4, 2, 3)
+        return torch.empty((B, Hb, Wb, C), device=feats.device, dtype=dtype).permute(0, 3, 1, 2)
+    shape = (B, V, C, Hb, Wb) if per_view else (B, C, Hb, Wb)
+    return torch.empty(shape, device=feats.device, dtype=dtype)
+
+
+def _check_calib(feats, K, Rt34, xs, ys):
+    B, V = feats.shape[:2]
+    for name, t, shape in (("K", K, (B, V, 3, 3)), ("Rt34", Rt34, (B, V, 3, 4))):
+        if tuple(t.shape) != shape or t.dtype != torch.float32 or not t.is_contiguous() or t.device != feats.device:
+            raise ValueError(f"{name} must be a contiguous float32 {shape} tensor on {feats.device}")
+    for name, t in (("xs", xs), ("ys", ys)):
+        if t.dim() != 1 or t.dtype != torch.float32 or not t.is_contiguous() or t.device != feats.device:
+            raise ValueError(f"{name} must be a contiguous 1-D float32 tensor on {feats.device}")
+
+
+@torch.library.custom_op("bevipm::warp_fuse", mutates_args=(), device_types="cuda")
+def warp_fuse(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+              img_h: int, img_w: int, mode: int, out_bf16: bool, variant: int) -> torch.Tensor:
+    """Fused IPM warp + view fusion (geometry.py:120-162 + fusion.py:17-22 of the reference).
+
+    feats [B,V,C,Hf,Wf] float32 / bfloat16, any strides (channels-last = the fast kernel).
+    Returns [B,C,Hb,Wb] (sum / mean / max) or [B,V,C,Hb,Wb] (mode NONE), channels-last in memory
+    when the features are, fp32 unless out_bf16.
+    """
+    if feats.dim() != 5:
+        raise ValueError("feats must be [B,V,C,Hf,Wf]")
+    if feats.dtype not in _DT:
+        raise TypeError(f"feats dtype {feats.dtype} is not supported (float32 / bfloat16)")
+    _check_calib(feats, K, Rt34, xs, ys)
+    L = _lib.load()
+    per_view = mode == _lib.NONE
+    Hb, Wb = ys.numel(), xs.numel()
+    out_dtype = torch.bfloat16 if out_bf16 else torch.float32
+    with torch.cuda.device(feats.device):
+        out = _alloc_out(feats, Hb, Wb, per_view, out_dtype, _is_channels_last5(feats))
+        d = _fill_desc(feats.shape, feats.stride(), _out_strides5(out, per_view), (Hb, Wb), (img_h, img_w), mode,
+                       _DT[feats.dtype], _DT[out_dtype], variant)
+        _lib.check(L.bevipm_warp_fuse_fwd(ctypes.byref(d), _ptr(feats), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys),
+                                          _ptr(out), ctypes.c_void_p(_stream_ptr(feats.device))))
+    return out
+
+
+@warp_fuse.register_fake
+def _(feats, K, Rt34, xs, ys, img_h, img_w, mode, out_bf16, variant):
+    B, V, C = feats.shape[:3]
+    Hb, Wb = ys.numel(), xs.numel()
+    dt = torch.bfloat16 if out_bf16 else torch.float32
+    shape = (B, V, C, Hb, Wb) if mode == _lib.NONE else (B, C, Hb, Wb)
+    return feats.new_empty(shape, dtype=dt)
+
+
+@torch.library.custom_op("bevipm::warp_fuse_bwd", mutates_args=(), device_types="cuda")
+def warp_fuse_bwd(grad_out: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                  feat_shape: Sequence[int], channels_last: bool, img_h: int, img_w: int, mode: int) -> torch.Tensor:
+    """fp32 gradient w.r.t. the features (scatter of the forward taps; train.py:243 reaches it)."""
+    L = _lib.load()
+    B, V, C, Hf, Wf = feat_shape
+    per_view = mode == _lib.NONE
+    if grad_out.dtype not in _DT:
+        grad_out = grad_out.float()
+    with torch.cuda.device(grad_out.device):
+        if channels_last:
+            g = torch.zeros((B, V, Hf, Wf, C), device=grad_out.device, dtype=torch.float32).permute(0, 1, 4, 2, 3)
+        else:
+            g = torch.zeros((B, V, C, Hf, Wf), device=grad_out.device, dtype=torch.float32)
+        d = _fill_desc(feat_shape, g.stride(), _out_strides5(grad_out, per_view), (ys.numel(), xs.numel()),
+                       (img_h, img_w), mode, _lib.F32, _DT[grad_out.dtype], 0)
+        _lib.check(L.bevipm_warp_fuse_bwd(ctypes.byref(d), _ptr(grad_out), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys),
+                                          _ptr(g), ctypes.c_void_p(_stream_ptr(grad_out.device))))
+    return g
+
+
+@warp_fuse_bwd.register_fake
+def _(grad_out, K, Rt34, xs, ys, feat_shape, channels_last, img_h, img_w, mode):
+    return grad_out.new_empty(tuple(feat_shape), dtype=torch.float32)
+
+
+def _setup_ctx(ctx, inputs, output):
+    feats, K, Rt34, xs, ys, img_h, img_w, mode, out_bf16, variant = inputs
+    ctx.save_for_backward(K, Rt34, xs, ys)
+    ctx.feat_shape = tuple(feats.shape)
+    ctx.feat_dtype = feats.dtype
+    ctx.channels_last = _is_channels_last5(feats)
+    ctx.args = (img_h, img_w, mode)
+
+
+def _backward(ctx, grad_out):
+    K, Rt34, xs, ys = ctx.saved_tensors
+    img_h, img_w, mode = ctx.args
+    g = warp_fuse_bwd(grad_out, K, Rt34, xs, ys, list(ctx.feat_shape), ctx.channels_last, img_h, img_w, mode)
+    return (g.to(ctx.feat_dtype),) + (None,) * 9
+
+
+warp_fuse.register_autograd(_backward, setup_context=_setup_ctx)
+
+
+# ---- the remaining entry points, as plain functions ----------------------------------------------
+
+def sample_coords(K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                  feat_hw: Tuple[int, int], img_size: Tuple[int, int]):
+    """ix, iy [B,V,Hb,Wb]: feature-pixel sample position of every BEV cell (device tensors)."""
+    L = _lib.load()
+    B, V = K.shape[:2]
+    Hb, Wb = ys.numel(), xs.numel()
+    ix = torch.empty((B, V, Hb, Wb), device=K.device, dtype=torch.float32)
+    iy = torch.empty_like(ix)
+    d = _fill_desc((B, V, 1, feat_hw[0], feat_hw[1]), (0,) * 5, (0,) * 5, (Hb, Wb), img_size, 0, 0, 0, 0)
+    with torch.cuda.device(K.device):
+        _lib.check(L.bevipm_sample_coords(ctypes.byref(d), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys), _ptr(ix), _ptr(iy),
+                                          ctypes.c_void_p(_stream_ptr(K.device))))
+    return ix, iy
+
+
+class _ToChannelsLast(torch.autograd.Function):
+    """Layout change only: the logical tensor is unchanged, so the gradient passes straight through."""
+
+    @staticmethod
+    def forward(ctx, feats):
+        return _to_channels_last5_impl(feats)
+
+    @staticmethod
+    def backward(ctx, grad):
+        return grad
+
+
+def to_channels_last5(feats: torch.Tensor) -> torch.Tensor:
+    """[B,V,C,H,W] NCHW-contiguous -> same logical tensor stored [B,V,H,W,C] (our transpose kernel)."""
+    if feats.dim() != 5 or not feats.is_cuda:
+        raise ValueError("to_channels_last5 wants a CUDA [B,V,C,H,W] tensor")
+    if _is_channels_last5(feats):
+        return feats
+    if feats.dtype not in _DT:
+        raise TypeError(f"dtype {feats.dtype} is not supported")
+    if feats.requires_grad and torch.is_grad_enabled():
+        return _ToChannelsLast.apply(feats)
+    return _to_channels_last5_impl(feats)
+
+
+def _to_channels_last5_impl(feats: torch.Tensor) -> torch.Tensor:
+    src = feats.detach().contiguous()
+    B, V, C, H, W = src.shape
+    dst = torch.empty((B, V, H, W, C), device=src.device, dtype=src.dtype)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().bevipm_nchw_to_nhwc(_ptr(src), _ptr(dst), B * V, C, H, W, _DT[src.dtype],
+                                                   ctypes.c_void_p(_stream_ptr(src.device))))
+    return dst.permute(0, 1, 4, 2, 3)
+
+
+def fuse_views(bev_maps: torch.Tensor, mode: str, out_dtype=None) -> torch.Tensor:
+    """SimpleFusion on materialised per-view maps [B,V,C,H,W] -> [B,C,H,W] (fusion.py:17-22)."""
+    if bev_maps.dim() != 5 or not bev_maps.is_cuda:
+        raise ValueError("fuse_views wants a CUDA [B,V,C,H,W] tensor")
+    if bev_maps.dtype not in _DT:
+        raise TypeError(f"dtype {bev_maps.dtype} is not supported")
+    B, V, C, H, W = bev_maps.shape
+    cl = _is_channels_last5(bev_maps) and not bev_maps.is_contiguous()
+    src = bev_maps.permute(0, 1, 3, 4, 2) if cl else bev_maps
+    src = src.contiguous()
+    out_dtype = out_dtype or bev_maps.dtype
+    out = torch.empty((B, H, W, C) if cl else (B, C, H, W), device=src.device, dtype=out_dtype)
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().bevipm_fuse_views(_ptr(src), _ptr(out), B, V, C * H * W, MODES[mode], _DT[src.dtype],
+                                                 _DT[out_dtype], ctypes.c_void_p(_stream_ptr(src.device))))
+    return out.permute(0, 3, 1, 2) if cl else out
+
+
+def warp_fuse_host(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                   img_size: Tuple[int, int], mode: str = "mean", out: torch.Tensor | None = None,
+                   out_dtype=None, variant: int = 0) -> torch.Tensor:
+    """Host-buffer call: feats [B,V,Hf,Wf,C] on the HOST (pinned for full PCIe rate) -> out [B,Hb,Wb,C]
+    on the host.  H2D, kernel and D2H are pipelined frame by frame inside the library."""
+    if feats.is_cuda or feats.dim() != 5 or not feats.is_contiguous():
+        raise ValueError("warp_fuse_host wants a contiguous host tensor [B,V,Hf,Wf,C]")
+    B, V, Hf, Wf, C = feats.shape
+    Hb, Wb = ys.numel(), xs.numel()
+    m = MODES[mode]
+    out_dtype = out_dtype or feats.dtype
+    shape = (B, V, Hb, Wb, C) if m == _lib.NONE else (B, Hb, Wb, C)
+    if out is None:
+        out = torch.empty(shape, dtype=out_dtype, pin_memory=True)
+    if tuple(out.shape) != shape or out.dtype != out_dtype or not out.is_contiguous() or out.is_cuda:
+        raise ValueError(f"out must be a contiguous host {out_dtype} tensor of shape {shape}")
+    Kc, Rc = K.contiguous().float().cpu(), Rt34.contiguous().float().cpu()
+    xc, yc = xs.contiguous().float().cpu(), ys.contiguous().float().cpu()
+    d = _fill_desc((B, V, C, Hf, Wf), (0,) * 5, (0,) * 5, (Hb, Wb), img_size, m, _DT[feats.dtype], _DT[out_dtype], variant)
+    _lib.check(_lib.load().bevipm_warp_fuse_host(ctypes.byref(d), _ptr(feats), _ptr(Kc), _ptr(Rc), _ptr(xc), _ptr(yc),
+                                                 _ptr(out)))
+    return out

@@ -1,0 +1,365 @@
+// bevipm_api.cu -- the C ABI declared in include/bevipm.h: argument checking, kernel choice,
+// launch.  No torch types, no allocation (except the host-entry staging arena), no device sync.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/bevipm.h"
+#include "ipm_aux.cuh"
+#include "ipm_fused.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<int64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+    return fail(BEVIPM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+#define CUDA_TRY(expr)                                       \
+    do {                                                     \
+        cudaError_t e__ = (expr);                            \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #expr); \
+    } while (0)
+
+using bevipm::FwdParams;
+
+int check_desc(const bevipm_desc* d) {
+    if (!d) return fail(BEVIPM_ERR_BAD_ARG, "desc is null");
+    if (d->B <= 0 || d->V <= 0 || d->C <= 0 || d->Hf <= 0 || d->Wf <= 0 || d->Hb <= 0 || d->Wb <= 0)
+        return fail(BEVIPM_ERR_BAD_ARG, "non-positive extent (B=%d V=%d C=%d Hf=%d Wf=%d Hb=%d Wb=%d)", d->B, d->V,
+                    d->C, d->Hf, d->Wf, d->Hb, d->Wb);
+    if (d->img_h <= 0 || d->img_w <= 0) return fail(BEVIPM_ERR_BAD_ARG, "img_size must be positive");
+    if (d->mode < BEVIPM_SUM || d->mode > BEVIPM_NONE) return fail(BEVIPM_ERR_BAD_ARG, "unknown mode %d", d->mode);
+    if ((d->in_dtype != BEVIPM_F32 && d->in_dtype != BEVIPM_BF16) ||
+        (d->out_dtype != BEVIPM_F32 && d->out_dtype != BEVIPM_BF16))
+        return fail(BEVIPM_ERR_BAD_ARG, "unknown dtype");
+    if (d->V > 32) return fail(BEVIPM_ERR_UNSUPPORTED, "V=%d views: this build stages at most 32 per patch", d->V);
+    if (d->B > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B=%d exceeds gridDim.z", d->B);
+    return 0;
+}
+
+FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, const float* Rt, const float* xs,
+                      const float* ys, void* out) {
+    FwdParams p;
+    p.feats = feats; p.out = out; p.K = K; p.Rt = Rt; p.xs = xs; p.ys = ys;
+    p.B = d->B; p.V = d->V; p.C = d->C; p.Hf = d->Hf; p.Wf = d->Wf; p.Hb = d->Hb; p.Wb = d->Wb;
+    p.sw = (float)((double)d->Wf / (double)d->img_w);  // geometry.py:151  python double -> fp32 scalar
+    p.sh = (float)((double)d->Hf / (double)d->img_h);  // geometry.py:152
+    p.mode = d->mode;
+    p.fs_b = d->fs_b; p.fs_v = d->fs_v; p.fs_c = d->fs_c; p.fs_y = d->fs_y; p.fs_x = d->fs_x;
+    p.os_b = d->os_b; p.os_v = d->os_v; p.os_c = d->os_c; p.os_y = d->os_y; p.os_x = d->os_x;
+    p.tiles_x = p.tiles_y = p.chunks = p.chunks_per_cta = 0;
+    return p;
+}
+
+int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---- fused NHWC fast path ---------------------------------------------------------------------
+struct Variant { int nv, cells, reuse; };
+// variant ids (bevipm_desc.variant); 0 = auto.  Kept small: every entry is 3 dtype pairs of code.
+constexpr Variant kVariants[] = {
+    {0, 0, 0},   // 0: auto
+    {1, 8, 0},   // 1
+    {1, 8, 1},   // 2
+    {2, 8, 0},   // 3  (fp32 features only)
+    {2, 8, 1},   // 4  (fp32 features only)
+    {1, 16, 0},  // 5  (fp32 features only)
+    {1, 16, 1},  // 6  (fp32 features only)
+    {1, 4, 0},   // 7
+    {1, 4, 1},   // 8
+    {2, 4, 0},   // 9
+    {2, 4, 1},   // 10
+};
+constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+constexpr int kTH = 8;
+
+template <typename TIn, typename TOut, int NV, int CELLS, int KMODE, bool REUSE>
+int launch_fused(FwdParams p, cudaStream_t st) {
+    constexpr int VE = bevipm::VecTraits<TIn>::VE;
+    constexpr int CH_CHUNK = 32 * NV * VE;
+    p.tiles_x = ceil_div(p.Wb, CELLS);
+    p.tiles_y = ceil_div(p.Hb, kTH);
+    p.chunks = ceil_div(p.C, CH_CHUNK);
+    p.chunks_per_cta = 1;
+    auto kern = bevipm::warp_fuse_nhwc_kernel<TIn, TOut, NV, CELLS, kTH, KMODE, REUSE>;
+    const size_t smem = (size_t)p.V * kTH * CELLS * sizeof(bevipm::CellTap) + (size_t)p.V * 9 * sizeof(float);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(p.tiles_x * p.tiles_y, ceil_div(p.chunks, p.chunks_per_cta), p.B);
+    kern<<<grid, 256, smem, st>>>(p);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+template <typename TIn, typename TOut>
+int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
+    constexpr bool kF32 = sizeof(TIn) == 4;
+    if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 8, bevipm::KM_MAX, false>(p, st);
+    if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 8, bevipm::KM_NONE, true>(p, st);
+    if (variant == 0) {
+        // default choice; revisited against ncu in profiles/
+        variant = 2;
+    }
+    switch (variant) {
+        case 1: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, false>(p, st);
+        case 2: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, true>(p, st);
+        case 7: return launch_fused<TIn, TOut, 1, 4, bevipm::KM_ACC, false>(p, st);
+        case 8: return launch_fused<TIn, TOut, 1, 4, bevipm::KM_ACC, true>(p, st);
+        case 9: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, false>(p, st);
+        case 10: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, true>(p, st);
+        default: break;
+    }
+    if constexpr (kF32) {
+        switch (variant) {
+            case 3: return launch_fused<TIn, TOut, 2, 8, bevipm::KM_ACC, false>(p, st);
+            case 4: return launch_fused<TIn, TOut, 2, 8, bevipm::KM_ACC, true>(p, st);
+            case 5: return launch_fused<TIn, TOut, 1, 16, bevipm::KM_ACC, false>(p, st);
+            case 6: return launch_fused<TIn, TOut, 1, 16, bevipm::KM_ACC, true>(p, st);
+            default: break;
+        }
+    }
+    return fail(BEVIPM_ERR_UNSUPPORTED, "variant %d is not built for this dtype", variant);
+}
+
+template <typename TIn, typename TOut>
+int launch_strided(FwdParams p, cudaStream_t st) {
+    using namespace bevipm;
+    p.tiles_x = ceil_div(p.Wb, kGenTW);
+    p.tiles_y = ceil_div(p.Hb, kGenTH);
+    const int c_per_cta = 16;
+    auto kern = warp_fuse_strided_kernel<TIn, TOut>;
+    const size_t smem = (size_t)p.V * kGenTH * kGenTW * sizeof(CellTap) + (size_t)p.V * 9 * sizeof(float);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(p.tiles_x * p.tiles_y, ceil_div(p.C, c_per_cta), p.B);
+    if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "C=%d too large for the strided kernel", p.C);
+    kern<<<grid, kGenTH * kGenTW, smem, st>>>(p, c_per_cta);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// the NHWC fast path needs channel-contiguous 16-byte vectors on both sides
+bool fast_path_ok(const bevipm_desc* d, const void* feats, const void* out) {
+    const int ve_in = d->in_dtype == BEVIPM_F32 ? 4 : 8;
+    const int ve_out = d->out_dtype == BEVIPM_F32 ? 4 : 8;
+    if (d->fs_c != 1 || d->os_c != 1) return false;
+    if (d->C % ve_in) return false;
+    const int64_t fs[] = {d->fs_b, d->fs_v, d->fs_y, d->fs_x};
+    for (int64_t s : fs) if (s % ve_in) return false;
+    // the store vector is VE_in elements of the OUT type: 16 B (f32->f32, bf16->bf16), 32 B (bf16->f32), 8 B (f32->bf16)
+    const int64_t os[] = {d->os_b, d->os_v, d->os_y, d->os_x};
+    const int oal = (d->in_dtype == BEVIPM_F32 && d->out_dtype == BEVIPM_BF16) ? 4 : ve_out;
+    for (int64_t s : os) if (s % oal) return false;
+    return aligned16(feats) && aligned16(out);
+}
+
+}  // namespace
+
+extern "C" {
+
+int bevipm_version(void) { return BEVIPM_VERSION; }
+const char* bevipm_last_error(void) { return g_err; }
+int64_t bevipm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int bevipm_warp_fuse_fwd(const bevipm_desc* d, const void* feats, const float* K, const float* Rt34, const float* xs,
+                         const float* ys, void* out, void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (!feats || !K || !Rt34 || !xs || !ys || !out) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (d->variant < 0 || d->variant >= kNumVariants) return fail(BEVIPM_ERR_BAD_ARG, "unknown variant %d", d->variant);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const FwdParams p = make_params(d, feats, K, Rt34, xs, ys, out);
+    const bool fast = fast_path_ok(d, feats, out);
+    if (d->variant > 0 && !fast) return fail(BEVIPM_ERR_UNSUPPORTED, "variant %d needs the channels-last fast path", d->variant);
+    const bool in32 = d->in_dtype == BEVIPM_F32, out32 = d->out_dtype == BEVIPM_F32;
+    if (fast) {
+        if (in32 && out32) return dispatch_fused<float, float>(p, d->variant, st);
+        if (!in32 && !out32) return dispatch_fused<__nv_bfloat16, __nv_bfloat16>(p, d->variant, st);
+        if (!in32 && out32) return dispatch_fused<__nv_bfloat16, float>(p, d->variant, st);
+    }
+    if (in32 && out32) return launch_strided<float, float>(p, st);
+    if (in32 && !out32) return launch_strided<float, __nv_bfloat16>(p, st);
+    if (!in32 && out32) return launch_strided<__nv_bfloat16, float>(p, st);
+    return launch_strided<__nv_bfloat16, __nv_bfloat16>(p, st);
+}
+
+int bevipm_warp_fuse_bwd(const bevipm_desc* d, const void* grad_out, const float* K, const float* Rt34, const float* xs,
+                         const float* ys, float* grad_feats, void* stream) {
+    using namespace bevipm;
+    if (int rc = check_desc(d)) return rc;
+    if (!grad_out || !K || !Rt34 || !xs || !ys || !grad_feats) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (d->mode == BEVIPM_MAX) return fail(BEVIPM_ERR_UNSUPPORTED, "max fusion has no backward in this library");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FwdParams p = make_params(d, grad_feats, K, Rt34, xs, ys, const_cast<void*>(grad_out));
+    p.tiles_x = ceil_div(p.Wb, kGenTW);
+    p.tiles_y = ceil_div(p.Hb, kGenTH);
+    const size_t smem = (size_t)p.V * kGenTH * kGenTW * sizeof(CellTap) + (size_t)p.V * 9 * sizeof(float);
+    const bool g32 = d->out_dtype == BEVIPM_F32;
+    bool vec = d->fs_c == 1 && d->os_c == 1 && d->C % 4 == 0 && aligned16(grad_feats);
+    const int64_t fs[] = {d->fs_b, d->fs_v, d->fs_y, d->fs_x};
+    for (int64_t s : fs) if (s % 4) vec = false;
+    const int c_per_cta = vec ? 128 : 16;
+    dim3 grid(p.tiles_x * p.tiles_y, ceil_div(p.C, c_per_cta), p.B);
+    if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "C=%d too large for the backward kernel", p.C);
+#define BEVIPM_LAUNCH_BWD(TG, VEC)                                                                              \
+    do {                                                                                                        \
+        auto kern = warp_fuse_bwd_kernel<TG, VEC>;                                                              \
+        if (smem > 48 * 1024)                                                                                   \
+            CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));       \
+        kern<<<grid, kGenTH * kGenTW, smem, st>>>(p, c_per_cta);                                                \
+    } while (0)
+    if (g32 && vec) BEVIPM_LAUNCH_BWD(float, true);
+    else if (g32) BEVIPM_LAUNCH_BWD(float, false);
+    else if (vec) BEVIPM_LAUNCH_BWD(__nv_bfloat16, true);
+    else BEVIPM_LAUNCH_BWD(__nv_bfloat16, false);
+#undef BEVIPM_LAUNCH_BWD
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bevipm_sample_coords(const bevipm_desc* d, const float* K, const float* Rt34, const float* xs, const float* ys,
+                         float* ix, float* iy, void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (!K || !Rt34 || !xs || !ys || !ix || !iy) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    const FwdParams p = make_params(d, nullptr, K, Rt34, xs, ys, nullptr);
+    dim3 grid(ceil_div(d->Hb * d->Wb, 256), d->B * d->V);
+    if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B*V too large");
+    bevipm::sample_coords_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(p, ix, iy);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bevipm_nchw_to_nhwc(const void* src, void* dst, int32_t N, int32_t C, int32_t H, int32_t W, int32_t dtype,
+                        void* stream) {
+    if (!src || !dst) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (N <= 0 || C <= 0 || H <= 0 || W <= 0) return fail(BEVIPM_ERR_BAD_ARG, "non-positive extent");
+    if (N > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "N=%d exceeds gridDim.z", N);
+    const int HW = H * W;
+    dim3 grid(ceil_div(HW, 32), ceil_div(C, 32), N);
+    if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "C too large");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (dtype == BEVIPM_F32)
+        bevipm::nchw_to_nhwc_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, C, HW);
+    else if (dtype == BEVIPM_BF16)
+        bevipm::nchw_to_nhwc_kernel<uint16_t><<<grid, 256, 0, st>>>((const uint16_t*)src, (uint16_t*)dst, C, HW);
+    else
+        return fail(BEVIPM_ERR_BAD_ARG, "unknown dtype");
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bevipm_fuse_views(const void* in, void* out, int64_t B, int32_t V, int64_t inner, int32_t mode, int32_t in_dtype,
+                      int32_t out_dtype, void* stream) {
+    if (!in || !out) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (B <= 0 || V <= 0 || inner <= 0) return fail(BEVIPM_ERR_BAD_ARG, "non-positive extent");
+    if (mode < BEVIPM_SUM || mode > BEVIPM_MAX) return fail(BEVIPM_ERR_BAD_ARG, "mode must be sum, mean or max");
+    if (B > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B exceeds gridDim.y");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long want = (inner + 255) / 256;
+    dim3 grid((unsigned)(want < 148 * 32 ? want : 148 * 32), (unsigned)B);
+    const bool i32 = in_dtype == BEVIPM_F32, o32 = out_dtype == BEVIPM_F32;
+    if (i32 && o32) bevipm::fuse_views_kernel<float, float><<<grid, 256, 0, st>>>((const float*)in, (float*)out, V, inner, mode);
+    else if (i32) bevipm::fuse_views_kernel<float, __nv_bfloat16><<<grid, 256, 0, st>>>((const float*)in, (__nv_bfloat16*)out, V, inner, mode);
+    else if (o32) bevipm::fuse_views_kernel<__nv_bfloat16, float><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (float*)out, V, inner, mode);
+    else bevipm::fuse_views_kernel<__nv_bfloat16, __nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, V, inner, mode);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- host-buffer entry: H2D -> kernel -> D2H, frame by frame, double buffered -----------------------
+namespace {
+struct HostArena {
+    void* feats[2] = {nullptr, nullptr};
+    void* out[2] = {nullptr, nullptr};
+    float* calib = nullptr;
+    size_t feat_bytes = 0, out_bytes = 0, calib_bytes = 0;
+    cudaStream_t st[2] = {nullptr, nullptr};
+    cudaEvent_t calib_ready = nullptr;
+    int device = -1;
+    void release() {
+        for (int s = 0; s < 2; ++s) {
+            if (feats[s]) cudaFree(feats[s]);
+            if (out[s]) cudaFree(out[s]);
+            if (st[s]) cudaStreamDestroy(st[s]);
+            feats[s] = out[s] = nullptr; st[s] = nullptr;
+        }
+        if (calib) cudaFree(calib);
+        if (calib_ready) cudaEventDestroy(calib_ready);
+        calib = nullptr; calib_ready = nullptr;
+        feat_bytes = out_bytes = calib_bytes = 0; device = -1;
+    }
+};
+thread_local HostArena g_arena;
+}  // namespace
+
+void bevipm_host_release(void) { g_arena.release(); }
+
+int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const float* K, const float* Rt34,
+                          const float* xs, const float* ys, void* out) {
+    if (int rc = check_desc(d_in)) return rc;
+    if (!feats || !K || !Rt34 || !xs || !ys || !out) return fail(BEVIPM_ERR_BAD_ARG, "null host pointer");
+    bevipm_desc d = *d_in;
+    const size_t ie = d.in_dtype == BEVIPM_F32 ? 4 : 2, oe = d.out_dtype == BEVIPM_F32 ? 4 : 2;
+    const size_t out_maps = d.mode == BEVIPM_NONE ? d.V : 1;
+    const size_t fbytes = (size_t)d.V * d.Hf * d.Wf * d.C * ie;          // one frame of features
+    const size_t obytes = out_maps * d.Hb * d.Wb * d.C * oe;             // one frame of BEV
+    const size_t cal_floats = (size_t)d.B * d.V * 21 + d.Wb + d.Hb;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    HostArena& A = g_arena;
+    if (A.device != dev || A.feat_bytes < fbytes || A.out_bytes < obytes || A.calib_bytes < cal_floats * 4) {
+        A.release();
+        for (int s = 0; s < 2; ++s) {
+            CUDA_TRY(cudaMalloc(&A.feats[s], fbytes));
+            CUDA_TRY(cudaMalloc(&A.out[s], obytes));
+            CUDA_TRY(cudaStreamCreateWithFlags(&A.st[s], cudaStreamNonBlocking));
+        }
+        CUDA_TRY(cudaMalloc(&A.calib, cal_floats * 4));
+        CUDA_TRY(cudaEventCreateWithFlags(&A.calib_ready, cudaEventDisableTiming));
+        A.feat_bytes = fbytes; A.out_bytes = obytes; A.calib_bytes = cal_floats * 4; A.device = dev;
+    }
+    float* dK = A.calib;
+    float* dRt = dK + (size_t)d.B * d.V * 9;
+    float* dxs = dRt + (size_t)d.B * d.V * 12;
+    float* dys = dxs + d.Wb;
+    CUDA_TRY(cudaMemcpyAsync(dK, K, (size_t)d.B * d.V * 9 * 4, cudaMemcpyHostToDevice, A.st[0]));
+    CUDA_TRY(cudaMemcpyAsync(dRt, Rt34, (size_t)d.B * d.V * 12 * 4, cudaMemcpyHostToDevice, A.st[0]));
+    CUDA_TRY(cudaMemcpyAsync(dxs, xs, (size_t)d.Wb * 4, cudaMemcpyHostToDevice, A.st[0]));
+    CUDA_TRY(cudaMemcpyAsync(dys, ys, (size_t)d.Hb * 4, cudaMemcpyHostToDevice, A.st[0]));
+    CUDA_TRY(cudaEventRecord(A.calib_ready, A.st[0]));
+    CUDA_TRY(cudaStreamWaitEvent(A.st[1], A.calib_ready, 0));
+    // one frame per launch, channels-last on the device
+    const int B = d.B;
+    d.B = 1;
+    d.fs_c = 1; d.fs_x = d.C; d.fs_y = (int64_t)d.Wf * d.C; d.fs_v = (int64_t)d.Hf * d.fs_y; d.fs_b = d.V * d.fs_v;
+    d.os_c = 1; d.os_x = d.C; d.os_y = (int64_t)d.Wb * d.C; d.os_v = (int64_t)d.Hb * d.os_y; d.os_b = out_maps * d.os_v;
+    for (int f = 0; f < B; ++f) {
+        const int s = f & 1;
+        CUDA_TRY(cudaMemcpyAsync(A.feats[s], (const char*)feats + (size_t)f * fbytes, fbytes, cudaMemcpyHostToDevice, A.st[s]));
+        if (int rc = bevipm_warp_fuse_fwd(&d, A.feats[s], dK + (size_t)f * d.V * 9, dRt + (size_t)f * d.V * 12, dxs, dys,
+                                          A.out[s], A.st[s]))
+            return rc;
+        CUDA_TRY(cudaMemcpyAsync((char*)out + (size_t)f * obytes, A.out[s], obytes, cudaMemcpyDeviceToHost, A.st[s]));
+    }
+    CUDA_TRY(cudaStreamSynchronize(A.st[0]));
+    CUDA_TRY(cudaStreamSynchronize(A.st[1]));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,206 @@
+// ipm_aux.cuh -- the kernels around the fused fast path: strided fallback forward, backward,
+// sample-coordinate dump, NCHW -> NHWC layout pre-pass.  All CUDA; there is no CPU path.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "ipm_fused.cuh"
+
+namespace bevipm {
+
+template <typename T> __device__ __forceinline__ float load_f32(const T* p);
+template <> __device__ __forceinline__ float load_f32<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_f32<__nv_bfloat16>(const __nv_bfloat16* p) {
+    return __bfloat162float(__ldg(p));
+}
+template <typename T> __device__ __forceinline__ void store_f32(T* p, float v);
+template <> __device__ __forceinline__ void store_f32<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void store_f32<__nv_bfloat16>(__nv_bfloat16* p, float v) {
+    *p = __float2bfloat16_rn(v);
+}
+
+constexpr int kGenTH = 4, kGenTW = 32;  // strided kernels: one thread per cell of a 4 x 32 patch
+
+// One view's bilinear value for one channel: fma(SE,se, fma(SW,sw, fma(NE,ne, NW*nw))).
+template <typename TIn>
+__device__ __forceinline__ float sample_scalar(const TIn* plane, const CellTap& t, long long fs_y, long long fs_x) {
+    const TIn* base = plane + (long long)t.y0 * fs_y + (long long)t.x0 * fs_x;
+    const float a = (t.flags & 1) ? load_f32(base) : 0.0f;
+    const float b = (t.flags & 2) ? load_f32(base + fs_x) : 0.0f;
+    const float c = (t.flags & 4) ? load_f32(base + fs_y) : 0.0f;
+    const float d = (t.flags & 8) ? load_f32(base + fs_y + fs_x) : 0.0f;
+    float r = __fmul_rn(a, t.nw);
+    r = __fmaf_rn(b, t.ne, r);
+    r = __fmaf_rn(c, t.sw, r);
+    r = __fmaf_rn(d, t.se, r);
+    return r;
+}
+
+// Any strides, any C (the NCHW-contiguous tensors the reference's encoder emits, odd channel
+// counts).  Lanes run along BEV x so NCHW stores coalesce; channels are looped per thread.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(kGenTH* kGenTW) warp_fuse_strided_kernel(const FwdParams p, int c_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellTap* taps = reinterpret_cast<CellTap*>(smem_raw);
+    float* sH = reinterpret_cast<float*>(taps + p.V * kGenTH * kGenTW);
+    const int b = blockIdx.z;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int i0 = ty * kGenTH, j0 = tx * kGenTW;
+    project_patch(p, b, i0, j0, kGenTH, kGenTW, taps, sH);
+    const int r = threadIdx.x / kGenTW, q = threadIdx.x % kGenTW;
+    const int i = i0 + r, j = j0 + q;
+    if (i >= p.Hb || j >= p.Wb) return;
+    const TIn* fb = reinterpret_cast<const TIn*>(p.feats) + (long long)b * p.fs_b;
+    TOut* ob = reinterpret_cast<TOut*>(p.out) + (long long)b * p.os_b + (long long)i * p.os_y + (long long)j * p.os_x;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float Vf = (float)p.V;
+    const int c_end = min(p.C, (int)(blockIdx.y + 1) * c_per_cta);
+    for (int c = blockIdx.y * c_per_cta; c < c_end; ++c) {
+        float acc = (p.mode == 2) ? -INFINITY : 0.0f;
+        for (int v = 0; v < p.V; ++v) {
+            const CellTap t = taps[(v * kGenTH + r) * kGenTW + q];
+            float s = 0.0f;
+            if (t.flags & kTapMask) s = sample_scalar(fb + (long long)v * p.fs_v + (long long)c * p.fs_c, t, p.fs_y, p.fs_x);
+            else if (t.flags & kNonFinite) s = qnan;
+            if (p.mode == 3) store_f32(ob + (long long)v * p.os_v + (long long)c * p.os_c, s);
+            else if (p.mode == 2) acc = (s > acc || s != s) ? s : acc;
+            else acc = __fadd_rn(acc, s);
+        }
+        if (p.mode == 1) acc = __fdiv_rn(acc, Vf);
+        if (p.mode != 3) store_f32(ob + (long long)c * p.os_c, acc);
+    }
+}
+
+// Backward w.r.t. the features: scatter of the same taps (autograd of geometry.py:161 followed
+// by fusion.py:18-21).  grad_feats is fp32 and pre-zeroed; out-strides describe grad_out.
+// VEC: channels-last on both sides, C % 4 == 0 -> lane owns 4 channels, red.global.add.v4.f32.
+template <typename TG, bool VEC>
+__global__ void __launch_bounds__(kGenTH* kGenTW) warp_fuse_bwd_kernel(const FwdParams p, int c_per_cta) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CellTap* taps = reinterpret_cast<CellTap*>(smem_raw);
+    float* sH = reinterpret_cast<float*>(taps + p.V * kGenTH * kGenTW);
+    const int b = blockIdx.z;
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int i0 = ty * kGenTH, j0 = tx * kGenTW;
+    project_patch(p, b, i0, j0, kGenTH, kGenTW, taps, sH);
+    const TG* gb = reinterpret_cast<const TG*>(p.out) + (long long)b * p.os_b;
+    float* fb = reinterpret_cast<float*>(const_cast<void*>(p.feats)) + (long long)b * p.fs_b;
+    const float Vf = (float)p.V;
+    const int c_begin = blockIdx.y * c_per_cta, c_end = min(p.C, c_begin + c_per_cta);
+    if constexpr (VEC) {
+        // warp r walks the 32 cells of its row; lanes own 4 consecutive channels each
+        const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int i = i0 + r;
+        if (i >= p.Hb) return;
+        for (int q = 0; q < kGenTW; ++q) {
+            const int j = j0 + q;
+            if (j >= p.Wb) break;
+            const TG* gc = gb + (long long)i * p.os_y + (long long)j * p.os_x;
+            for (int c = c_begin + lane * 4; c < c_end; c += 128) {
+                float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.mode != 3) {
+                    g = make_float4(load_f32(gc + c), load_f32(gc + c + 1), load_f32(gc + c + 2), load_f32(gc + c + 3));
+                    if (p.mode == 1) g = make_float4(__fdiv_rn(g.x, Vf), __fdiv_rn(g.y, Vf), __fdiv_rn(g.z, Vf), __fdiv_rn(g.w, Vf));
+                }
+                for (int v = 0; v < p.V; ++v) {
+                    const CellTap t = taps[(v * kGenTH + r) * kGenTW + q];
+                    if (!(t.flags & kTapMask)) continue;
+                    if (p.mode == 3) {
+                        const TG* gv = gc + (long long)v * p.os_v + c;
+                        g = make_float4(load_f32(gv), load_f32(gv + 1), load_f32(gv + 2), load_f32(gv + 3));
+                    }
+                    float* base = fb + (long long)v * p.fs_v + (long long)t.y0 * p.fs_y + (long long)t.x0 * p.fs_x + c;
+                    const float w[4] = {t.nw, t.ne, t.sw, t.se};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (!((t.flags >> k) & 1)) continue;
+                        float* tp = base + (k & 1 ? p.fs_x : 0) + (k & 2 ? p.fs_y : 0);
+                        atomicAdd(reinterpret_cast<float4*>(tp),
+                                  make_float4(__fmul_rn(w[k], g.x), __fmul_rn(w[k], g.y), __fmul_rn(w[k], g.z), __fmul_rn(w[k], g.w)));
+                    }
+                }
+            }
+        }
+    } else {
+        const int r = threadIdx.x / kGenTW, q = threadIdx.x % kGenTW;
+        const int i = i0 + r, j = j0 + q;
+        if (i >= p.Hb || j >= p.Wb) return;
+        const TG* gc = gb + (long long)i * p.os_y + (long long)j * p.os_x;
+        for (int c = c_begin; c < c_end; ++c) {
+            float g = 0.0f;
+            if (p.mode != 3) {
+                g = load_f32(gc + (long long)c * p.os_c);
+                if (p.mode == 1) g = __fdiv_rn(g, Vf);
+            }
+            for (int v = 0; v < p.V; ++v) {
+                const CellTap t = taps[(v * kGenTH + r) * kGenTW + q];
+                if (!(t.flags & kTapMask)) continue;
+                if (p.mode == 3) g = load_f32(gc + (long long)v * p.os_v + (long long)c * p.os_c);
+                float* base = fb + (long long)v * p.fs_v + (long long)c * p.fs_c + (long long)t.y0 * p.fs_y + (long long)t.x0 * p.fs_x;
+                if (t.flags & 1) atomicAdd(base, __fmul_rn(t.nw, g));
+                if (t.flags & 2) atomicAdd(base + p.fs_x, __fmul_rn(t.ne, g));
+                if (t.flags & 4) atomicAdd(base + p.fs_y, __fmul_rn(t.sw, g));
+                if (t.flags & 8) atomicAdd(base + p.fs_y + p.fs_x, __fmul_rn(t.se, g));
+            }
+        }
+    }
+}
+
+// ix, iy [B,V,Hb,Wb]: what phase A computes, exported for tests and for the byte counter.
+__global__ void sample_coords_kernel(const FwdParams p, float* __restrict__ ix, float* __restrict__ iy) {
+    const int bv = blockIdx.y;
+    __shared__ float H[9];
+    if (threadIdx.x == 0) homography(p.K + 9 * bv, p.Rt + 12 * bv, H);
+    __syncthreads();
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= p.Hb * p.Wb) return;
+    const int i = cell / p.Wb, j = cell - i * p.Wb;
+    float x, y;
+    cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y);
+    ix[(long long)bv * p.Hb * p.Wb + cell] = x;
+    iy[(long long)bv * p.Hb * p.Wb + cell] = y;
+}
+
+// fusion.py:17-22 on materialised maps: in [B,V,inner] -> out [B,inner]; sequential over v.
+template <typename TIn, typename TOut>
+__global__ void __launch_bounds__(256) fuse_views_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int V,
+                                                         long long inner, int mode) {
+    const long long b = blockIdx.y;
+    const TIn* ib = in + b * V * inner;
+    TOut* ob = out + b * inner;
+    const float Vf = (float)V;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < inner; e += (long long)gridDim.x * blockDim.x) {
+        float acc = load_f32(ib + e);
+        for (int v = 1; v < V; ++v) {
+            const float s = load_f32(ib + (long long)v * inner + e);
+            if (mode == 2) acc = (s > acc || s != s) ? s : acc;
+            else acc = __fadd_rn(acc, s);
+        }
+        if (mode == 1) acc = __fdiv_rn(acc, Vf);
+        store_f32(ob + e, acc);
+    }
+}
+
+// [N,C,HW] -> [N,HW,C]   (the encoder's NCHW maps, cnn_encoder.py:65-70, into the fast path's layout)
+template <typename T>
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+    __shared__ T tile[32][33];
+    const long long n = blockIdx.z;
+    const int c0 = blockIdx.y * 32, s0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const T* sp = src + n * (long long)C * HW;
+    T* dp = dst + n * (long long)C * HW;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = c0 + ty + 8 * k, s = s0 + tx;
+        if (c < C && s < HW) tile[ty + 8 * k][tx] = sp[(long long)c * HW + s];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int s = s0 + ty + 8 * k, c = c0 + tx;
+        if (c < C && s < HW) dp[(long long)s * C + c] = tile[tx][ty + 8 * k];
+    }
+}
+
+}  // namespace bevipm
