@@ -1,5 +1,6 @@
 // bevipm_api.cu -- the C ABI declared in include/bevipm.h: argument checking, kernel choice,
 // launch.  No torch types, no allocation (except the host-entry staging arena), no device sync.
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -8,6 +9,7 @@
 #include "../../include/bevipm.h"
 #include "ipm_aux.cuh"
 #include "ipm_fused.cuh"
+#include "ipm_list.cuh"
 
 namespace {
 
@@ -59,32 +61,40 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
     p.mode = d->mode;
     p.fs_b = d->fs_b; p.fs_v = d->fs_v; p.fs_c = d->fs_c; p.fs_y = d->fs_y; p.fs_x = d->fs_x;
     p.os_b = d->os_b; p.os_v = d->os_v; p.os_c = d->os_c; p.os_y = d->os_y; p.os_x = d->os_x;
-    p.tiles_x = p.tiles_y = p.chunks = p.chunks_per_cta = 0;
+    p.tiles_x = p.tiles_y = p.chunks = p.chunks_per_cta = p.chunk_groups = p.total_tiles = 0;
+    p.fsy16 = p.fsx16 = 0;
+    p.rcpV = 0.0f;
     return p;
 }
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- fused NHWC fast path ---------------------------------------------------------------------
-struct Variant { int nv, cells, reuse; };
-// variant ids (bevipm_desc.variant); 0 = auto.  Kept small: every entry is 3 dtype pairs of code.
+// variant ids (bevipm_desc.variant); 0 = auto.  {vectors per lane, cells per warp walk, min CTAs/SM}
+struct Variant { int nv, cells, minb, pipe; };
 constexpr Variant kVariants[] = {
-    {0, 0, 0},   // 0: auto
-    {1, 8, 0},   // 1
-    {1, 8, 1},   // 2
-    {2, 8, 0},   // 3  (fp32 features only)
-    {2, 8, 1},   // 4  (fp32 features only)
-    {1, 16, 0},  // 5  (fp32 features only)
-    {1, 16, 1},  // 6  (fp32 features only)
-    {1, 4, 0},   // 7
-    {1, 4, 1},   // 8
-    {2, 4, 0},   // 9
-    {2, 4, 1},   // 10
+    {0, 0, 0, 0},  // 0: auto
+    {1, 2, 4, 0},  // 1
+    {1, 2, 3, 1},  // 2
+    {2, 4, 2, 0},  // 3
+    {1, 4, 3, 0},  // 4
+    {2, 2, 2, 0},  // 5
+    {2, 2, 2, 1},  // 6
+    {4, 1, 2, 0},  // 7
+    {2, 1, 3, 0},  // 8
+    {4, 2, 1, 0},  // 9
+    {1, 4, 2, 1},  // 10
+    {1, 2, 4, 0},  // 11..14: loads-only timing probes (results are NOT the fusion)
+    {2, 2, 2, 0},
+    {2, 2, 2, 1},
+    {4, 2, 2, 0},
+    {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0},  // 15..19 unused
+    {4, 4, 2, 1}, {4, 4, 3, 1}, {2, 4, 3, 1}, {2, 4, 4, 1}, {1, 4, 6, 1}, {2, 8, 2, 1}, {4, 8, 1, 1}, {1, 4, 4, 1},  // 20..27: list kernel {NV, warps, minb}
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kTH = 8;
 
-template <typename TIn, typename TOut, int NV, int CELLS, int KMODE, bool REUSE>
+template <typename TIn, typename TOut, int NV, int CELLS, int KMODE, int MINB, bool PIPE>
 int launch_fused(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int CH_CHUNK = 32 * NV * VE;
@@ -92,7 +102,10 @@ int launch_fused(FwdParams p, cudaStream_t st) {
     p.tiles_y = ceil_div(p.Hb, kTH);
     p.chunks = ceil_div(p.C, CH_CHUNK);
     p.chunks_per_cta = 1;
-    auto kern = bevipm::warp_fuse_nhwc_kernel<TIn, TOut, NV, CELLS, kTH, KMODE, REUSE>;
+    p.fsy16 = (int)(p.fs_y / VE);
+    p.fsx16 = (int)(p.fs_x / VE);
+    p.rcpV = 1.0f / (float)p.V;
+    auto kern = bevipm::warp_fuse_nhwc_kernel<TIn, TOut, NV, CELLS, kTH, KMODE, MINB, PIPE>;
     const size_t smem = (size_t)p.V * kTH * CELLS * sizeof(bevipm::CellTap) + (size_t)p.V * 9 * sizeof(float);
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(p.tiles_x * p.tiles_y, ceil_div(p.chunks, p.chunks_per_cta), p.B);
@@ -102,34 +115,63 @@ int launch_fused(FwdParams p, cudaStream_t st) {
     return 0;
 }
 
+// ---- list kernel (branch-free, software-pipelined) ---------------------------------------------------
+template <typename TIn, typename TOut, int NV, int KMODE, int NWARPS, int MINB>
+int launch_list(FwdParams p, cudaStream_t st) {
+    constexpr int VE = bevipm::VecTraits<TIn>::VE;
+    constexpr int CH_CHUNK = 32 * NV * VE;
+    const int tw = std::max(1, std::min(bevipm::kListCells, bevipm::kListMaxSteps / p.V));
+    p.tiles_x = ceil_div(p.Wb, tw);
+    p.tiles_y = ceil_div(p.Hb, NWARPS);
+    p.chunks = ceil_div(p.C, CH_CHUNK);
+    p.fsy16 = (int)(p.fs_y / VE);
+    p.fsx16 = (int)(p.fs_x / VE);
+    p.rcpV = 1.0f / (float)p.V;
+    auto kern = bevipm::warp_fuse_list_kernel<TIn, TOut, NV, KMODE, NWARPS, MINB>;
+    const size_t smem = (size_t)NWARPS * (bevipm::kListMaxSteps + 2) * sizeof(bevipm::StepRec);
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (p.chunks > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "C=%d too large", p.C);
+    dim3 grid(p.tiles_x * p.tiles_y, p.chunks, p.B);
+    kern<<<grid, NWARPS * 32, smem, st>>>(p, tw);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename TIn, typename TOut>
 int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
-    constexpr bool kF32 = sizeof(TIn) == 4;
-    if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 8, bevipm::KM_MAX, false>(p, st);
-    if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 8, bevipm::KM_NONE, true>(p, st);
+    if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st);
+    if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
     if (variant == 0) {
         // default choice; revisited against ncu in profiles/
-        variant = 2;
+        variant = 7;
     }
     switch (variant) {
-        case 1: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, false>(p, st);
-        case 2: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, true>(p, st);
-        case 7: return launch_fused<TIn, TOut, 1, 4, bevipm::KM_ACC, false>(p, st);
-        case 8: return launch_fused<TIn, TOut, 1, 4, bevipm::KM_ACC, true>(p, st);
-        case 9: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, false>(p, st);
-        case 10: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, true>(p, st);
+        case 1: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_ACC, 4, false>(p, st);
+        case 2: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, 2, false>(p, st);
+        case 3: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, 2, false>(p, st);
+        case 4: return launch_fused<TIn, TOut, 1, 4, bevipm::KM_ACC, 3, false>(p, st);
+        case 5: return launch_fused<TIn, TOut, 2, 2, bevipm::KM_ACC, 2, false>(p, st);
+        case 6: return launch_fused<TIn, TOut, 2, 8, bevipm::KM_ACC, 1, false>(p, st);
+        case 7: return launch_fused<TIn, TOut, 4, 1, bevipm::KM_ACC, 2, false>(p, st);
+        case 8: return launch_fused<TIn, TOut, 2, 1, bevipm::KM_ACC, 3, false>(p, st);
+        case 9: return launch_fused<TIn, TOut, 4, 2, bevipm::KM_ACC, 1, false>(p, st);
+        case 10: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, 1, false>(p, st);
+        case 20: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 4, 2>(p, st);
+        case 21: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 4, 3>(p, st);
+        case 22: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 4, 3>(p, st);
+        case 23: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 4, 4>(p, st);
+        case 24: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 6>(p, st);
+        case 25: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 8, 2>(p, st);
+        case 26: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 8, 1>(p, st);
+        case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
+        case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes
+        case 12: return launch_fused<TIn, TOut, 2, 2, bevipm::KM_PROBE, 2, false>(p, st);
+        case 13: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_PROBE, 2, false>(p, st);
+        case 14: return launch_fused<TIn, TOut, 4, 2, bevipm::KM_PROBE, 2, false>(p, st);
         default: break;
     }
-    if constexpr (kF32) {
-        switch (variant) {
-            case 3: return launch_fused<TIn, TOut, 2, 8, bevipm::KM_ACC, false>(p, st);
-            case 4: return launch_fused<TIn, TOut, 2, 8, bevipm::KM_ACC, true>(p, st);
-            case 5: return launch_fused<TIn, TOut, 1, 16, bevipm::KM_ACC, false>(p, st);
-            case 6: return launch_fused<TIn, TOut, 1, 16, bevipm::KM_ACC, true>(p, st);
-            default: break;
-        }
-    }
-    return fail(BEVIPM_ERR_UNSUPPORTED, "variant %d is not built for this dtype", variant);
+    return fail(BEVIPM_ERR_UNSUPPORTED, "variant %d is not built", variant);
 }
 
 template <typename TIn, typename TOut>
@@ -159,6 +201,8 @@ bool fast_path_ok(const bevipm_desc* d, const void* feats, const void* out) {
     if (d->C % ve_in) return false;
     const int64_t fs[] = {d->fs_b, d->fs_v, d->fs_y, d->fs_x};
     for (int64_t s : fs) if (s % ve_in) return false;
+    // tap offsets inside one view are kept as 32-bit counts of 16-byte vectors
+    if (d->fs_y < 0 || d->fs_x < 0 || ((d->Hf + 2) * (d->fs_y / ve_in) + (d->Wf + 2) * (d->fs_x / ve_in)) > 0x7fffffffLL) return false;
     // the store vector is VE_in elements of the OUT type: 16 B (f32->f32, bf16->bf16), 32 B (bf16->f32), 8 B (f32->bf16)
     const int64_t os[] = {d->os_b, d->os_v, d->os_y, d->os_x};
     const int oal = (d->in_dtype == BEVIPM_F32 && d->out_dtype == BEVIPM_BF16) ? 4 : ve_out;

@@ -10,13 +10,13 @@
 //            thread and parked in shared memory as a 32-byte CellTap
 //   phase B: a warp owns (patch row, channel chunk); lane l owns NV 16-byte channel vectors
 //            (vector n = channels [chunk0 + (n*32 + l)*VE, +VE)), so every tap is read by the
-//            warp as NV fully coalesced 512-byte requests.  The warp walks its CELLS cells
-//            view by view, accumulating across views in registers, and writes each BEV cell
-//            exactly once with 16-byte stores.
-//   REUSE: while walking a row the 2x2 texel block is kept in registers; because the cell is
-//            warp-uniform the "did the block move?" test is a uniform branch, and a one-texel
-//            move reloads only the new column/row.  This cuts L1 requests 2-5x when the BEV
-//            grid is denser than the source map (BASELINE config 3).
+//            warp as NV fully coalesced 512-byte requests.  The warp walks (view, cell) steps,
+//            accumulating across views in registers, and writes each BEV cell exactly once with
+//            16-byte stores.  The taps of step s+1 are requested before step s is blended
+//            (two register buffers), so the loads of one step hide behind the math of the last.
+//   The cell is warp-uniform, so "are all four taps inside the map?" is a uniform branch:
+//   interior cells take loads without predicates, border cells a predicated zero-filling path,
+//   cells a view does not see cost two LDS and a branch.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -40,10 +40,14 @@ struct FwdParams {
     long long os_b, os_v, os_c, os_y, os_x;
     int tiles_x, tiles_y;
     int chunks;          // channel chunks in total
-    int chunks_per_cta;  // channel chunks one CTA walks
+    int chunks_per_cta;  // channel chunks one CTA walks (strided / backward kernels)
+    int chunk_groups;    // fused kernel: channel chunks == tile groups along C
+    int total_tiles;     // fused kernel: tiles_x * tiles_y * chunk_groups * B
+    int fsy16, fsx16;    // fs_y, fs_x in 16-byte units (fast path)
+    float rcpV;          // RN(1 / V) for the exact mean division
 };
 
-enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2 };
+enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2, KM_PROBE = 3 /* timing probe: loads only, no blend */ };
 
 // ---- 16-byte vector <-> fp32 pairs -------------------------------------------------------
 template <typename T> struct VecTraits;
@@ -67,9 +71,7 @@ template <> struct VecTraits<__nv_bfloat16> {
     }
 };
 
-__device__ __forceinline__ uint4 ldg16(const void* p) {
-    return __ldg(reinterpret_cast<const uint4*>(p));
-}
+__device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
 
 // P float2 pairs -> global memory as TOut, streaming (written once, never re-read by us)
 template <typename TOut, int P>
@@ -93,6 +95,17 @@ __device__ __forceinline__ void store_pairs(TOut* dst, const float2 (&f)[P]) {
     }
 }
 
+// x / V, correctly rounded, in three FMA-pipe ops instead of the ~10-instruction IEEE division
+// sequence: q = RN(x * r), e = x - q * V (exact in one fma), result = RN(q + e * r) with
+// r = RN(1/V).  This is Markstein's correction step and returns the IEEE quotient whenever no
+// intermediate underflows; tiny |x| (and zeros) take the library division.
+__device__ __forceinline__ float div_exact(float x, float Vf, float r) {
+    if (fabsf(x) < 1e-30f) return __fdiv_rn(x, Vf);
+    const float q = __fmul_rn(x, r);
+    const float e = __fmaf_rn(-q, Vf, x);
+    return __fmaf_rn(e, r, q);
+}
+
 // ---- phase A: project the patch ------------------------------------------------------------
 __device__ __forceinline__ void project_patch(const FwdParams& p, int b, int i0, int j0, int TH, int TW,
                                               CellTap* taps, float* sH) {
@@ -110,9 +123,9 @@ __device__ __forceinline__ void project_patch(const FwdParams& p, int b, int i0,
         if (i < p.Hb && j < p.Wb) {
             float ix, iy;
             cell_coord(sH + 9 * v, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, Wm, Hm, ix, iy);
-            t = make_tap(ix, iy, p.Wf, p.Hf);
+            t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
         } else {
-            t.x0 = t.y0 = -2; t.nw = t.ne = t.sw = t.se = 0.0f; t.flags = 0; t.pad = 0;
+            t.x0 = t.y0 = -2; t.nw = t.ne = t.sw = t.se = 0.0f; t.flags = 0; t.off16 = 0;
         }
         taps[idx] = t;
     }
@@ -120,10 +133,55 @@ __device__ __forceinline__ void project_patch(const FwdParams& p, int b, int i0,
 }
 
 // ---- phase B helpers --------------------------------------------------------------------
+// What phase B keeps in registers for one (view, cell) step: the first 24 bytes of the CellTap.
+struct StepHdr {
+    int off16, flags;
+    float nw, ne, sw, se;
+};
+
+__device__ __forceinline__ StepHdr read_hdr(const CellTap* t) {
+    const int4 a = *reinterpret_cast<const int4*>(t);
+    const float2 b = *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(t) + 16);
+    StepHdr h;
+    h.off16 = a.x; h.flags = a.y; h.nw = __int_as_float(a.z); h.ne = __int_as_float(a.w); h.sw = b.x; h.se = b.y;
+    return h;
+}
+
+// Request the four taps of one (view, cell) step.  `vb` points at this lane's first vector of the
+// view; tap k lives at vb[off16 + (k&1)*dx16 + (k>>1)*dy16], vector n 32 vectors further.  Indices
+// are 32-bit so each address is one IMAD.WIDE.
+template <int NV>
+__device__ __forceinline__ void request_taps(uint4 (&raw)[4][NV], const uint4* vb, const StepHdr& h, bool full,
+                                             const bool (&cok)[NV], int dx16, int dy16) {
+    const int tm = h.flags & kTapMask;
+    if (tm == kTapMask && full) {  // interior cell, full channel chunk: no predicates, no zero fill
+        const uint4* p0 = vb + h.off16;
+        const uint4* p1 = vb + (h.off16 + dx16);
+        const uint4* p2 = vb + (h.off16 + dy16);
+        const uint4* p3 = vb + (h.off16 + dy16 + dx16);
+#pragma unroll
+        for (int n = 0; n < NV; ++n) {
+            raw[0][n] = ldg16(p0 + n * 32);
+            raw[1][n] = ldg16(p1 + n * 32);
+            raw[2][n] = ldg16(p2 + n * 32);
+            raw[3][n] = ldg16(p3 + n * 32);
+        }
+    } else if (tm) {               // border cell (taps outside the map read as zero) or partial chunk
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap) {
+            const bool ok = (tm >> tap) & 1;
+            const uint4* tp = vb + (h.off16 + ((tap & 1) ? dx16 : 0) + ((tap & 2) ? dy16 : 0));
+#pragma unroll
+            for (int n = 0; n < NV; ++n)
+                raw[tap][n] = (ok && cok[n]) ? ldg16(tp + n * 32) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+}
+
 // out_v = fma(SE,se, fma(SW,sw, fma(NE,ne, NW*nw)))  -- ATen's interpolation order, two channels
 // per instruction with the sm_100 packed-fp32 pipe (FMUL2 / FFMA2: IEEE fp32 per element).
 template <typename TIn, int NV>
-__device__ __forceinline__ void blend(const uint4 (&raw)[4][NV], const CellTap& t,
+__device__ __forceinline__ void blend(const uint4 (&raw)[4][NV], const StepHdr& t,
                                       float2 (&o)[NV][VecTraits<TIn>::P]) {
     constexpr int P = VecTraits<TIn>::P;
     const float2 nw = make_float2(t.nw, t.nw), ne = make_float2(t.ne, t.ne);
@@ -146,11 +204,81 @@ __device__ __forceinline__ void blend(const uint4 (&raw)[4][NV], const CellTap& 
     }
 }
 
-template <typename TIn, typename TOut, int NV, int CELLS, int TH, int KMODE, bool REUSE>
-__global__ void __launch_bounds__(256) warp_fuse_nhwc_kernel(const FwdParams p) {
+// Fold one step's per-view value into the cell's accumulator / write it out (NONE).
+template <typename TIn, typename TOut, int NV, int KMODE>
+__device__ __forceinline__ void consume(const uint4 (&raw)[4][NV], const StepHdr& t,
+                                        float2 (&acc)[NV][VecTraits<TIn>::P], TOut* oc, const int (&cvec)[NV],
+                                        const bool (&cok)[NV], bool store_ok) {
+    constexpr int P = VecTraits<TIn>::P;
+    if constexpr (KMODE == KM_PROBE) {
+        // measurement aid (never dispatched by the public modes): fold the raw taps with integer adds
+        if (t.flags & kTapMask) {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                const uint4 s = raw[0][n], u = raw[1][n], w = raw[2][n], z = raw[3][n];
+                acc[n][0].x = __uint_as_float(__float_as_uint(acc[n][0].x) + s.x + u.x + w.x + z.x);
+                acc[n][0].y = __uint_as_float(__float_as_uint(acc[n][0].y) + s.y + u.y + w.y + z.y);
+                acc[n][1].x = __uint_as_float(__float_as_uint(acc[n][1].x) + s.z + u.z + w.z + z.z);
+                acc[n][1].y = __uint_as_float(__float_as_uint(acc[n][1].y) + s.w + u.w + w.w + z.w);
+            }
+        }
+        return;
+    }
+    float2 o[NV][P];
+    bool have = false;
+    if (t.flags & kTapMask) {
+        blend<TIn, NV>(raw, t, o);
+        have = true;
+    } else if (t.flags & kNonFinite) {
+        // reference: weights are NaN and 0 * NaN = NaN reaches every channel
+        const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+        for (int n = 0; n < NV; ++n)
+#pragma unroll
+            for (int e = 0; e < P; ++e) o[n][e] = make_float2(qnan, qnan);
+        have = true;
+    }
+    if constexpr (KMODE == KM_ACC) {
+        // fusion.py:18-21  sequential fp32 accumulation over views (a view that misses the cell
+        // contributes exactly +0: skipped)
+        if (have) {
+#pragma unroll
+            for (int n = 0; n < NV; ++n)
+#pragma unroll
+                for (int e = 0; e < P; ++e) acc[n][e] = __fadd2_rn(acc[n][e], o[n][e]);
+        }
+    } else if constexpr (KMODE == KM_MAX) {
+        // fusion.py:22  the zeros of out-of-view cells take part; NaN propagates
+#pragma unroll
+        for (int n = 0; n < NV; ++n)
+#pragma unroll
+            for (int e = 0; e < P; ++e) {
+                const float sx = have ? o[n][e].x : 0.0f, sy = have ? o[n][e].y : 0.0f;
+                float2& m = acc[n][e];
+                m.x = (sx > m.x || sx != sx) ? sx : m.x;
+                m.y = (sy > m.y || sy != sy) ? sy : m.y;
+            }
+    } else {
+        // per-view maps (geometry.py:162): written straight out, zero where the view misses
+        if (store_ok) {
+#pragma unroll
+            for (int n = 0; n < NV; ++n) {
+                if (!cok[n]) continue;
+                float2 z[P];
+#pragma unroll
+                for (int e = 0; e < P; ++e) z[e] = have ? o[n][e] : make_float2(0.0f, 0.0f);
+                store_pairs<TOut, P>(oc + cvec[n], z);
+            }
+        }
+    }
+}
+
+template <typename TIn, typename TOut, int NV, int CELLS, int TH, int KMODE, int MINB, bool PIPE>
+__global__ void __launch_bounds__(256, MINB) warp_fuse_nhwc_kernel(const FwdParams p) {
     using VT = VecTraits<TIn>;
     constexpr int VE = VT::VE, P = VT::P;
     constexpr int CH_CHUNK = 32 * NV * VE;
+    static_assert(!PIPE || CELLS % 2 == 0, "the two tap buffers alternate per cell");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CellTap* taps = reinterpret_cast<CellTap*>(smem_raw);
     float* sH = reinterpret_cast<float*>(taps + p.V * TH * CELLS);
@@ -164,7 +292,8 @@ __global__ void __launch_bounds__(256) warp_fuse_nhwc_kernel(const FwdParams p) 
     const int nwarps = blockDim.x >> 5;
     const TIn* fb = reinterpret_cast<const TIn*>(p.feats) + (long long)b * p.fs_b;
     TOut* ob = reinterpret_cast<TOut*>(p.out) + (long long)b * p.os_b;
-    const float qnan = __int_as_float(0x7fc00000);
+    const int dx16 = p.fsx16, dy16 = p.fsy16;
+    const long long fsv16 = p.fs_v / VE;
 
     const int items = TH * p.chunks_per_cta;
     for (int item = warp; item < items; item += nwarps) {
@@ -179,6 +308,10 @@ __global__ void __launch_bounds__(256) warp_fuse_nhwc_kernel(const FwdParams p) 
             cvec[n] = k * CH_CHUNK + (n * 32 + lane) * VE;
             cok[n] = cvec[n] < p.C;
         }
+        const bool full = (k + 1) * CH_CHUNK <= p.C;
+        // this lane's first vector of view 0
+        const uint4* vb = reinterpret_cast<const uint4*>(fb) + (k * (CH_CHUNK / VE) + lane);
+        TOut* orow = ob + (long long)i * p.os_y + (long long)j0 * p.os_x;
 
         float2 acc[CELLS][NV][P];
         if constexpr (KMODE != KM_NONE) {
@@ -191,116 +324,66 @@ __global__ void __launch_bounds__(256) warp_fuse_nhwc_kernel(const FwdParams p) 
                     for (int e = 0; e < P; ++e) acc[q][n][e] = make_float2(init, init);
         }
 
-        for (int v = 0; v < p.V; ++v) {
-            const TIn* fv = fb + (long long)v * p.fs_v;
-            const CellTap* row = taps + (v * TH + r) * CELLS;
-            uint4 raw[4][NV];
-            int cx = -(1 << 24), cy = -(1 << 24);  // origin of the cached 2x2 block (REUSE); "none yet"
+        const CellTap* row = taps + r * CELLS;  // view 0; + TH*CELLS per view
+        if constexpr (PIPE) {
+            // two register buffers: step s = v*CELLS + q uses buffer (q & 1); CELLS is even
+            uint4 raw[2][4][NV];
+            StepHdr hdr[2];
+            hdr[0] = read_hdr(row);
+            request_taps<NV>(raw[0], vb, hdr[0], full, cok, dx16, dy16);
+            for (int v = 0; v < p.V; ++v) {
 #pragma unroll
-            for (int q = 0; q < CELLS; ++q) {
-                const CellTap t = row[q];  // warp-uniform broadcast, 2 x LDS.128
-                float2 o[NV][P];
-                bool have = false;
-                if (t.flags & kTapMask) {
-                    const TIn* base = fv + (long long)t.y0 * p.fs_y + (long long)t.x0 * p.fs_x;
-                    // tap k lives at base + (k&1)*fs_x + (k>>1)*fs_y
-                    auto load_tap = [&](int tap) {
-                        const bool ok = (t.flags >> tap) & 1;
-                        const TIn* tp = base + (tap & 1 ? p.fs_x : 0) + (tap & 2 ? p.fs_y : 0);
-#pragma unroll
-                        for (int n = 0; n < NV; ++n)
-                            raw[tap][n] = (ok && cok[n]) ? ldg16(tp + cvec[n]) : make_uint4(0, 0, 0, 0);
-                    };
-                    if constexpr (REUSE) {
-                        const int dx = t.x0 - cx, dy = t.y0 - cy;
-                        if (dx == 0 && dy == 0) {
-                            // same 2x2 block: nothing to fetch
-                        } else if (dy == 0 && dx == 1) {
-#pragma unroll
-                            for (int n = 0; n < NV; ++n) { raw[0][n] = raw[1][n]; raw[2][n] = raw[3][n]; }
-                            load_tap(1); load_tap(3);
-                        } else if (dy == 0 && dx == -1) {
-#pragma unroll
-                            for (int n = 0; n < NV; ++n) { raw[1][n] = raw[0][n]; raw[3][n] = raw[2][n]; }
-                            load_tap(0); load_tap(2);
-                        } else if (dx == 0 && dy == 1) {
-#pragma unroll
-                            for (int n = 0; n < NV; ++n) { raw[0][n] = raw[2][n]; raw[1][n] = raw[3][n]; }
-                            load_tap(2); load_tap(3);
-                        } else if (dx == 0 && dy == -1) {
-#pragma unroll
-                            for (int n = 0; n < NV; ++n) { raw[2][n] = raw[0][n]; raw[3][n] = raw[1][n]; }
-                            load_tap(0); load_tap(1);
-                        } else {
-                            load_tap(0); load_tap(1); load_tap(2); load_tap(3);
-                        }
-                        cx = t.x0; cy = t.y0;
-                    } else {
-                        load_tap(0); load_tap(1); load_tap(2); load_tap(3);
+                for (int q = 0; q < CELLS; ++q) {
+                    const int cur = q & 1, nxt = cur ^ 1;
+                    if (q + 1 < CELLS) {
+                        hdr[nxt] = read_hdr(row + q + 1);
+                        request_taps<NV>(raw[nxt], vb, hdr[nxt], full, cok, dx16, dy16);
+                    } else if (v + 1 < p.V) {
+                        hdr[nxt] = read_hdr(row + TH * CELLS);
+                        request_taps<NV>(raw[nxt], vb + fsv16, hdr[nxt], full, cok, dx16, dy16);
                     }
-                    blend<TIn, NV>(raw, t, o);
-                    have = true;
-                } else if (t.flags & kNonFinite) {
-                    // reference: weights are NaN and 0 * NaN = NaN reaches every channel
-#pragma unroll
-                    for (int n = 0; n < NV; ++n)
-#pragma unroll
-                        for (int e = 0; e < P; ++e) o[n][e] = make_float2(qnan, qnan);
-                    have = true;
+                    consume<TIn, TOut, NV, KMODE>(raw[cur], hdr[cur], acc[q], orow + (long long)v * p.os_v + (long long)q * p.os_x,
+                                                  cvec, cok, j0 + q < p.Wb);
                 }
-                if constexpr (KMODE == KM_ACC) {
-                    // fusion.py:18-21  sequential fp32 accumulation over views (a view that misses
-                    // the cell contributes exactly +0: skipped)
-                    if (have) {
+                row += TH * CELLS;
+                vb += fsv16;
+            }
+        } else {
+            for (int v = 0; v < p.V; ++v) {
+                // Walking a BEV row, consecutive cells often fall into the SAME 2x2 texel block when the
+                // BEV grid is denser than the source map: then the registers already hold the taps and
+                // the step costs no L1 request at all (warp-uniform test).
+                uint4 raw[4][NV];
+                int held_off = 0, held_flags = 0;  // flags 0 = nothing held
 #pragma unroll
-                        for (int n = 0; n < NV; ++n)
-#pragma unroll
-                            for (int e = 0; e < P; ++e) acc[q][n][e] = __fadd2_rn(acc[q][n][e], o[n][e]);
+                for (int q = 0; q < CELLS; ++q) {
+                    const StepHdr h = read_hdr(row + q);
+                    if (CELLS == 1 || h.off16 != held_off || h.flags != held_flags) {
+                        request_taps<NV>(raw, vb, h, full, cok, dx16, dy16);
+                        if (h.flags & kTapMask) { held_off = h.off16; held_flags = h.flags; }
                     }
-                } else if constexpr (KMODE == KM_MAX) {
-                    // fusion.py:22  the zeros of out-of-view cells take part; NaN propagates
-#pragma unroll
-                    for (int n = 0; n < NV; ++n)
-#pragma unroll
-                        for (int e = 0; e < P; ++e) {
-                            const float sx = have ? o[n][e].x : 0.0f, sy = have ? o[n][e].y : 0.0f;
-                            float2& m = acc[q][n][e];
-                            m.x = (sx > m.x || sx != sx) ? sx : m.x;
-                            m.y = (sy > m.y || sy != sy) ? sy : m.y;
-                        }
-                } else {
-                    // per-view maps (geometry.py:162): written straight out, zero where the view misses
-                    const int j = j0 + q;
-                    if (j < p.Wb) {
-                        TOut* oc = ob + (long long)v * p.os_v + (long long)i * p.os_y + (long long)j * p.os_x;
-#pragma unroll
-                        for (int n = 0; n < NV; ++n) {
-                            if (!cok[n]) continue;
-                            float2 z[P];
-#pragma unroll
-                            for (int e = 0; e < P; ++e) z[e] = have ? o[n][e] : make_float2(0.0f, 0.0f);
-                            store_pairs<TOut, P>(oc + cvec[n], z);
-                        }
-                    }
+                    consume<TIn, TOut, NV, KMODE>(raw, h, acc[q], orow + (long long)v * p.os_v + (long long)q * p.os_x, cvec, cok,
+                                                  j0 + q < p.Wb);
                 }
+                row += TH * CELLS;
+                vb += fsv16;
             }
         }
 
         if constexpr (KMODE != KM_NONE) {
-            const float Vf = (float)p.V;
+            const float Vf = (float)p.V;  // (KM_PROBE stores its folded bits the same way)
 #pragma unroll
             for (int q = 0; q < CELLS; ++q) {
-                const int j = j0 + q;
-                if (j >= p.Wb) continue;
-                TOut* oc = ob + (long long)i * p.os_y + (long long)j * p.os_x;
+                if (j0 + q >= p.Wb) continue;
+                TOut* oc = orow + (long long)q * p.os_x;
 #pragma unroll
                 for (int n = 0; n < NV; ++n) {
                     if (!cok[n]) continue;
-                    if (KMODE == KM_ACC && p.mode == 1 /* BEVIPM_MEAN: sum / V, IEEE division */) {
+                    if (KMODE == KM_ACC && p.mode == 1 /* BEVIPM_MEAN: sum / V, IEEE quotient */) {
 #pragma unroll
                         for (int e = 0; e < P; ++e) {
-                            acc[q][n][e].x = __fdiv_rn(acc[q][n][e].x, Vf);
-                            acc[q][n][e].y = __fdiv_rn(acc[q][n][e].y, Vf);
+                            acc[q][n][e].x = div_exact(acc[q][n][e].x, Vf, p.rcpV);
+                            acc[q][n][e].y = div_exact(acc[q][n][e].y, Vf, p.rcpV);
                         }
                     }
                     store_pairs<TOut, P>(oc + cvec[n], acc[q][n]);

@@ -12,10 +12,11 @@ namespace bevipm {
 // What one BEV cell needs from one view: the NW texel index, the four bilinear weights and
 // which taps exist.  32 bytes so a warp-uniform read is two LDS.128 broadcasts.
 struct __align__(16) CellTap {
-    int x0, y0;            // NW texel (clamped to [-2, size] so the int conversion is always defined)
-    float nw, ne, sw, se;  // ATen grid-sampler weights
+    // first 16 bytes + next 8: all the fused kernel reads per step (LDS.128 + LDS.64)
+    int off16;             // NW texel offset from the view's base in 16-byte units (NHWC fast path only)
     int flags;             // bit0..3: NW, NE, SW, SE inside the map; bit4: non-finite coordinate
-    int pad;
+    float nw, ne, sw, se;  // ATen grid-sampler weights
+    int x0, y0;            // NW texel (clamped to [-2, size] so the int conversion is always defined)
 };
 static_assert(sizeof(CellTap) == 32, "CellTap must stay 32 bytes");
 
@@ -63,7 +64,7 @@ __device__ __forceinline__ void cell_coord(const float* H, float x, float y, flo
 }
 
 // Bilinear set-up of ATen's grid sampler: floor, distances, weight products, per-tap bounds.
-__device__ __forceinline__ CellTap make_tap(float ix, float iy, int Wf, int Hf) {
+__device__ __forceinline__ CellTap make_tap(float ix, float iy, int Wf, int Hf, int fsy16 = 0, int fsx16 = 0) {
     CellTap t;
     const float x0 = floorf(ix), y0 = floorf(iy);
     const float wx = __fsub_rn(ix, x0), ex = __fsub_rn(1.0f, wx);
@@ -84,7 +85,7 @@ __device__ __forceinline__ CellTap make_tap(float ix, float iy, int Wf, int Hf) 
     t.x0 = (int)fminf(fmaxf(x0, -2.0f), Wm);
     t.y0 = (int)fminf(fmaxf(y0, -2.0f), Hm);
     if (!finite) { t.x0 = -2; t.y0 = -2; }
-    t.pad = 0;
+    t.off16 = t.y0 * fsy16 + t.x0 * fsx16;
     return t;
 }
 
