@@ -118,6 +118,18 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "samples_under_load": len(loaded)}
 
 
+def ncu_traffic(workload: str, variant: int):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    p = ROOT / "profiles" / "traffic.json"
+    try:
+        t = json.loads(p.read_text()).get(workload)
+        if t and int(t.get("variant", -1)) == int(variant):
+            return int(t["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
+
+
 def measured_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -313,9 +325,9 @@ def run_ours(args, wl):
                 "variant": args.variant, "arithmetic": "fp32 (bit-exact op chain of the reference), storage as named"}),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "traffic": ncu_traffic(wl.name, args.variant), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "algorithmic_bytes_per_frame": alg["b_alg"], "b_full_per_frame": alg["b_full"],
-                         "frac_of_nominal_8TBs": achieved / 8000.0, "kernel": "warp_fuse_nhwc_kernel"},
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "kernel": "warp_fuse_list_kernel (auto variant) unless --variant forces another"},
             "clocks": clocks,
         }
         if e2e:

@@ -128,7 +128,10 @@ int launch_list(FwdParams p, cudaStream_t st) {
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
     auto kern = bevipm::warp_fuse_list_kernel<TIn, TOut, NV, KMODE, NWARPS, MINB>;
-    const size_t smem = (size_t)NWARPS * (bevipm::kListMaxSteps + 2) * sizeof(bevipm::StepRec);
+    const size_t smem = (size_t)NWARPS * bevipm::kListWarpBytes;
+    // tap offsets (view offset included) are 32-bit counts of 16-byte vectors
+    if ((long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * p.fsy16 + (long long)(p.Wf + 2) * p.fsx16 > 0x7fffffffLL)
+        return fail(BEVIPM_ERR_UNSUPPORTED, "feature maps too large for the list kernel's 32-bit tap offsets");
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (p.chunks > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "C=%d too large", p.C);
     dim3 grid(p.tiles_x * p.tiles_y, p.chunks, p.B);
@@ -143,8 +146,15 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st);
     if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
     if (variant == 0) {
-        // default choice; revisited against ncu in profiles/
-        variant = 7;
+        // Default = the list kernel, with as many 16-byte vectors per lane as one texel holds (up to 4):
+        // measured best on every BASELINE shape (profiles/sweep_r01.md): texel 2 KB (c1, c2) -> NV 4,
+        // 512 B (c3) -> NV 1.  Feature maps too large for its 32-bit offsets fall back to the tile kernel.
+        const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
+        const long long span = (long long)p.V * (p.fs_v / bevipm::VecTraits<TIn>::VE) +
+                               (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
+                               (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
+        if (span > 0x7fffffffLL) variant = 7;
+        else variant = texel_bytes >= 2048 ? 21 : (texel_bytes >= 1024 ? 23 : 27);
     }
     switch (variant) {
         case 1: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_ACC, 4, false>(p, st);
