@@ -147,7 +147,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
     if (variant == 0) {
         // Default = the list kernel, with as many 16-byte vectors per lane as one texel holds (up to 4):
-        // measured best on every BASELINE shape (profiles/sweep_r01.md): texel 2 KB (c1, c2) -> NV 4,
+        // measured best on every BASELINE shape (profiles/r01_notes.md): texel 2 KB (c1, c2) -> NV 4,
         // 512 B (c3) -> NV 1.  Feature maps too large for its 32-bit offsets fall back to the tile kernel.
         const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
         const long long span = (long long)p.V * (p.fs_v / bevipm::VecTraits<TIn>::VE) +
