@@ -106,6 +106,24 @@ int bevipm_fuse_views(const void *in, void *out, int64_t B, int32_t V, int64_t i
                       int32_t in_dtype, int32_t out_dtype, void *stream);
 
 /*
+ * Phase-2 follow-on: multi-view, multi-head deformable-attention sampling (the slot the reference's
+ * AttentionFusion placeholder reserves, fusion.py:25-36; semantics = Deformable-DETR's MSDeformAttn with
+ * one level per camera view, see csrc/deform_attn.cuh).  All device pointers:
+ *   value  [B,S,M,D] value_dtype, S = sum_l H_l*W_l     shapes [L,2] int32 (H,W)   level_start [L] int64
+ *   loc    [B,Q,M,L,P,2] f32, (x,y) in [0,1]            attn   [B,Q,M,L,P] f32      out [B,Q,M*D] out_dtype
+ * D * sizeof(value element) must be a multiple of 16 and at most 512 bytes.
+ */
+typedef struct bevipm_deform_desc {
+    int32_t B, Q, M, D, L, P;
+    int32_t value_dtype, out_dtype; /* bevipm_dtype */
+    int64_t S;
+} bevipm_deform_desc;
+
+int bevipm_deform_attn_fwd(const bevipm_deform_desc *d, const void *value, const int32_t *shapes,
+                           const int64_t *level_start, const float *loc, const float *attn, void *out,
+                           void *stream);
+
+/*
  * Host-buffer entry (the call a non-torch integrator makes, and what bench.py's e2e times):
  * feats/out are HOST pointers (pinned for full PCIe rate) laid out as feats [B,V,Hf,Wf,C] and
  * out [B,Hb,Wb,C] ([B,V,Hb,Wb,C] for NONE); K, Rt34, xs, ys are host arrays.  Frames are streamed

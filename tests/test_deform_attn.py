@@ -1,0 +1,94 @@
+"""Deformable-attention sampling kernel vs the from-spec oracle (parity unpinned by the reference, which
+only has a placeholder: fusion.py:25-36).  Tolerances: fp32 <= 1e-5, bf16 <= 1e-2, max-normalised."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import deform_attn_oracle as dorc
+
+
+def _case(B, Q, M, D, shapes, P, seed, spread=0.6):
+    g = torch.Generator().manual_seed(seed)
+    S = sum(h * w for h, w in shapes)
+    value = torch.randn(B, S, M, D, generator=g)
+    L = len(shapes)
+    loc = 0.5 + spread * (torch.rand(B, Q, M, L, P, 2, generator=g) - 0.5) * 2     # some land outside [0,1]
+    aw = torch.softmax(torch.randn(B, Q, M, L * P, generator=g), dim=-1).view(B, Q, M, L, P)
+    return value, loc, aw
+
+
+def test_two_oracle_forms_agree():
+    shapes = [(5, 7), (4, 6), (3, 3)]
+    value, loc, aw = _case(1, 6, 2, 4, shapes, 2, seed=0)
+    a = dorc.deform_attn_grid_sample(value, shapes, loc, aw)
+    b = dorc.deform_attn_scalar(value, shapes, loc, aw)
+    assert float((a - b).abs().max()) <= 1e-5 * float(b.abs().max())
+
+
+def test_oracle_known_answers():
+    # constant value map, all samples strictly inside -> output = sum of attention weights = 1
+    shapes = [(6, 8)]
+    value = torch.ones(1, 48, 1, 4)
+    loc = torch.full((1, 3, 1, 1, 2, 2), 0.5)
+    aw = torch.tensor([0.25, 0.75]).view(1, 1, 1, 1, 2).expand(1, 3, 1, 1, 2)
+    out = dorc.deform_attn_grid_sample(value, shapes, loc, aw)
+    assert torch.allclose(out, torch.ones_like(out), atol=1e-6)
+    # everything far outside -> zero
+    out = dorc.deform_attn_grid_sample(value, shapes, loc + 5.0, aw)
+    assert float(out.abs().max()) == 0.0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 1e-2)])
+@pytest.mark.parametrize("M,D", [(8, 32), (3, 8), (1, 64), (2, 128)])
+def test_kernel_matches_oracle(dtype, tol, M, D):
+    from bevipm import ops
+    shapes = [(9, 13), (7, 10), (5, 5), (12, 4)]
+    value, loc, aw = _case(2, 37, M, D, shapes, 4, seed=3)
+    value = value.to(dtype)
+    want = dorc.deform_attn_grid_sample(value.float(), shapes, loc, aw)
+    sh = torch.tensor(shapes, dtype=torch.int32)
+    start = torch.tensor(np.concatenate([[0], np.cumsum([h * w for h, w in shapes])[:-1]]), dtype=torch.int64)
+    out = ops.deform_attn(value.cuda(), sh.cuda(), start.cuda(), loc.cuda(), aw.cuda(), out_dtype=torch.float32).cpu()
+    assert out.shape == want.shape
+    assert float((out - want).abs().max()) <= tol * float(want.abs().max())
+    if dtype == torch.bfloat16:
+        # bf16 value in fp32 arithmetic: as tight as the fp32 case against the oracle fed the same rounded values
+        assert float((out - want).abs().max()) <= 1e-5 * float(want.abs().max())
+
+
+@pytest.mark.gpu
+def test_kernel_config4_shape_properties():
+    """BASELINE config 3: 120x360 queries, 8 heads x 4 points x 7 views, 256 ch bf16 (views as 135x240 maps)."""
+    from bevipm import ops
+    B, Q, M, D, L, P = 1, 120 * 360, 8, 32, 7, 4
+    shapes = [(135, 240)] * L
+    S = sum(h * w for h, w in shapes)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    value = torch.randn(B, S, M, D, device="cuda", generator=g).bfloat16()
+    loc = torch.rand(B, Q, M, L, P, 2, device="cuda", generator=g) * 1.2 - 0.1
+    aw = torch.softmax(torch.randn(B, Q, M, L * P, device="cuda", generator=g), dim=-1).view(B, Q, M, L, P)
+    sh = torch.tensor(shapes, dtype=torch.int32, device="cuda")
+    start = torch.arange(L, device="cuda", dtype=torch.int64) * (135 * 240)
+    out = ops.deform_attn(value, sh, start, loc, aw)
+    assert out.shape == (B, Q, M * D) and out.dtype == torch.bfloat16
+    # a slice of queries against the oracle
+    sl = slice(1000, 1256)
+    want = dorc.deform_attn_grid_sample(value.float().cpu(), shapes, loc[:, sl].cpu(), aw[:, sl].cpu())
+    assert float((out[:, sl].float().cpu() - want).abs().max()) <= 1e-2 * float(want.abs().max())
+    # linear in the attention weights, linear in the values (power-of-two scale: exact in fp32 output)
+    o32 = ops.deform_attn(value, sh, start, loc, aw, out_dtype=torch.float32)
+    assert torch.equal(ops.deform_attn(value * 2, sh, start, loc, aw, out_dtype=torch.float32), o32 * 2)
+    assert torch.equal(ops.deform_attn(value, sh, start, loc, aw * 0.5, out_dtype=torch.float32), o32 * 0.5)
+    # constant value maps and in-map samples -> every channel equals the sum of the weights (= 1)
+    ones = torch.ones_like(value)
+    inside = loc.clamp(0.05, 0.95)
+    c = ops.deform_attn(ones, sh, start, inside, aw, out_dtype=torch.float32)
+    assert float((c - 1).abs().max()) <= 1e-5
+
+
+def test_cpu_tensors_rejected():
+    from bevipm import ops
+    with pytest.raises(RuntimeError):
+        ops.deform_attn(torch.zeros(1, 4, 1, 8), torch.tensor([[2, 2]]), torch.tensor([0]), torch.zeros(1, 1, 1, 1, 1, 2),
+                        torch.ones(1, 1, 1, 1, 1))

@@ -28,8 +28,13 @@ class Desc(ctypes.Structure):
 EXPORTS = (
     "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
-    "bevipm_warp_fuse_host", "bevipm_host_release",
+    "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd",
 )
+
+class DeformDesc(ctypes.Structure):
+    """struct bevipm_deform_desc (include/bevipm.h)."""
+    _fields_ = [(n, ctypes.c_int32) for n in ("B", "Q", "M", "D", "L", "P", "value_dtype", "out_dtype")] + [("S", ctypes.c_int64)]
+
 
 _lib = None
 
@@ -56,6 +61,8 @@ def load() -> ctypes.CDLL:
                                     ctypes.c_int32, ctypes.c_int32, vp]
     L.bevipm_warp_fuse_host.argtypes = [dp, vp, fp, fp, fp, fp, vp]
     L.bevipm_host_release.restype = None
+    L.bevipm_deform_attn_fwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, vp]
+    L.bevipm_deform_attn_fwd.restype = ctypes.c_int
     for name in ("bevipm_warp_fuse_fwd", "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc",
                  "bevipm_fuse_views", "bevipm_warp_fuse_host"):
         getattr(L, name).restype = ctypes.c_int

@@ -234,3 +234,56 @@ class ConcatFusion(FusionModule):
     def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
         B, V, C, H, W = bev_maps.shape
         return bev_maps.reshape(B, V * C, H, W)
+
+
+class DeformAttnFusion(FusionModule):
+    """Phase-2 BEV fusion (the slot of the reference's AttentionFusion placeholder, fusion.py:25-36):
+    every BEV cell is a query that samples `points` locations per head from EACH view's BEV-warped map
+    around its own position (MVDeTr-style deformable attention, one level per camera view).
+
+    forward(bev_maps [B,V,C,H,W]) -> [B,C,H,W].  The projections are ordinary nn.Linear layers; the
+    sampling itself (B*H*W*heads*V*points bilinear gathers) runs in `bevipm_deform_attn_fwd`.
+    Forward only: use it for inference, or fine-tune the projections with the sampling detached.
+    """
+
+    def __init__(self, channels: int, views: int, heads: int = 8, points: int = 4):
+        super().__init__()
+        assert channels % heads == 0
+        self.channels, self.views, self.heads, self.points = channels, views, heads, points
+        self.sampling_offsets = nn.Linear(channels, heads * views * points * 2)
+        self.attention_weights = nn.Linear(channels, heads * views * points)
+        self.value_proj = nn.Linear(channels, channels)
+        self.output_proj = nn.Linear(channels, channels)
+        nn.init.zeros_(self.sampling_offsets.weight)
+        # Deformable-DETR's initialisation: points fan out on a ring around the query
+        import math
+        th = torch.arange(heads, dtype=torch.float32) * (2.0 * math.pi / heads)
+        grid = torch.stack([th.cos(), th.sin()], -1)
+        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(heads, 1, 1, 2).repeat(1, views, points, 1)
+        for i in range(points):
+            grid[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(grid.reshape(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+
+    @torch.no_grad()
+    def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
+        B, V, C, H, W = bev_maps.shape
+        assert V == self.views and C == self.channels
+        M, P, D = self.heads, self.points, C // self.heads
+        maps = bev_maps.permute(0, 1, 3, 4, 2)                                 # [B,V,H,W,C]
+        query = maps.mean(dim=1).reshape(B, H * W, C)                          # mean-fused BEV as the query
+        value = self.value_proj(maps.reshape(B, V * H * W, C)).view(B, V * H * W, M, D)
+        off = self.sampling_offsets(query).view(B, H * W, M, V, P, 2)
+        aw = torch.softmax(self.attention_weights(query).view(B, H * W, M, V * P), -1).view(B, H * W, M, V, P)
+        ys, xs = torch.meshgrid(torch.arange(H, device=maps.device), torch.arange(W, device=maps.device), indexing="ij")
+        ref = torch.stack([(xs + 0.5) / W, (ys + 0.5) / H], -1).reshape(1, H * W, 1, 1, 1, 2).to(off.dtype)
+        loc = ref + off / torch.tensor([W, H], device=maps.device, dtype=off.dtype)
+        shapes = torch.tensor([[H, W]] * V, dtype=torch.int32, device=maps.device)
+        start = torch.arange(V, device=maps.device, dtype=torch.int64) * (H * W)
+        if value.dtype not in (torch.float32, torch.bfloat16):
+            value = value.float()
+        out = ops.deform_attn(value, shapes, start, loc, aw, out_dtype=value.dtype)  # [B,Q,C]
+        out = self.output_proj(out.to(query.dtype))
+        return out.view(B, H, W, C).permute(0, 3, 1, 2)

@@ -239,3 +239,40 @@ def warp_fuse_host(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs:
     _lib.check(_lib.load().bevipm_warp_fuse_host(ctypes.byref(d), _ptr(feats), _ptr(Kc), _ptr(Rc), _ptr(xc), _ptr(yc),
                                                  _ptr(out)))
     return out
+
+
+# ---- Phase-2 follow-on: deformable-attention sampling ---------------------------------------------------
+
+def deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
+                sampling_locations: torch.Tensor, attention_weights: torch.Tensor, out_dtype=None) -> torch.Tensor:
+    """MSDeformAttn forward (Deformable-DETR semantics, one level per camera view).
+
+    value [B,S,M,D] float32/bfloat16, spatial_shapes [L,2] (H,W), level_start_index [L],
+    sampling_locations [B,Q,M,L,P,2] in [0,1], attention_weights [B,Q,M,L,P]  ->  [B,Q,M*D].
+    Forward only (inference fusion); CUDA tensors only.
+    """
+    if not value.is_cuda:
+        raise RuntimeError("bevipm runs on CUDA tensors only: there is no CPU implementation of this path")
+    if value.dim() != 4 or sampling_locations.dim() != 6 or attention_weights.dim() != 5:
+        raise ValueError("expected value [B,S,M,D], sampling_locations [B,Q,M,L,P,2], attention_weights [B,Q,M,L,P]")
+    if value.dtype not in _DT:
+        raise TypeError(f"value dtype {value.dtype} is not supported (float32 / bfloat16)")
+    B, S, M, D = value.shape
+    _, Q, M2, Lv, P, two = sampling_locations.shape
+    if M2 != M or two != 2 or tuple(attention_weights.shape) != (B, Q, M, Lv, P) or spatial_shapes.shape != (Lv, 2):
+        raise ValueError("inconsistent deformable-attention shapes")
+    dev = value.device
+    value = value.contiguous()
+    loc = sampling_locations.to(device=dev, dtype=torch.float32).contiguous()
+    aw = attention_weights.to(device=dev, dtype=torch.float32).contiguous()
+    shp = spatial_shapes.to(device=dev, dtype=torch.int32).contiguous()
+    start = level_start_index.to(device=dev, dtype=torch.int64).contiguous()
+    out_dtype = out_dtype or value.dtype
+    out = torch.empty((B, Q, M * D), device=dev, dtype=out_dtype)
+    d = _lib.DeformDesc()
+    d.B, d.Q, d.M, d.D, d.L, d.P = B, Q, M, D, Lv, P
+    d.value_dtype, d.out_dtype, d.S = _DT[value.dtype], _DT[out_dtype], S
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bevipm_deform_attn_fwd(ctypes.byref(d), _ptr(value), _ptr(shp), _ptr(start), _ptr(loc), _ptr(aw),
+                                                      _ptr(out), ctypes.c_void_p(_stream_ptr(dev))))
+    return out
