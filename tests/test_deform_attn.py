@@ -92,3 +92,33 @@ def test_cpu_tensors_rejected():
     with pytest.raises(RuntimeError):
         ops.deform_attn(torch.zeros(1, 4, 1, 8), torch.tensor([[2, 2]]), torch.tensor([0]), torch.zeros(1, 1, 1, 1, 1, 2),
                         torch.ones(1, 1, 1, 1, 1))
+
+
+@pytest.mark.gpu
+def test_fusion_module_matches_oracle_composition():
+    """DeformAttnFusion = torch projections + our sampling kernel; the same projections on the CPU with the
+    oracle doing the sampling must agree."""
+    import bevipm
+    torch.manual_seed(0)
+    B, V, C, H, W = 2, 3, 64, 10, 14
+    mod = bevipm.DeformAttnFusion(C, V, heads=4, points=2)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.2)
+    maps = torch.randn(B, V, C, H, W)
+    out = mod.cuda()(maps.cuda()).cpu()
+    assert out.shape == (B, C, H, W)
+    mod = mod.cpu()
+    with torch.no_grad():
+        M, P, D = 4, 2, C // 4
+        m2 = maps.permute(0, 1, 3, 4, 2)
+        query = m2.mean(dim=1).reshape(B, H * W, C)
+        value = mod.value_proj(m2.reshape(B, V * H * W, C)).view(B, V * H * W, M, D)
+        off = mod.sampling_offsets(query).view(B, H * W, M, V, P, 2)
+        aw = torch.softmax(mod.attention_weights(query).view(B, H * W, M, V * P), -1).view(B, H * W, M, V, P)
+        ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        ref = torch.stack([(xs + 0.5) / W, (ys + 0.5) / H], -1).reshape(1, H * W, 1, 1, 1, 2).float()
+        loc = ref + off / torch.tensor([W, H], dtype=torch.float32)
+        smp = dorc.deform_attn_grid_sample(value, [(H, W)] * V, loc, aw)
+        want = mod.output_proj(smp).view(B, H, W, C).permute(0, 3, 1, 2)
+    assert float((out - want).abs().max()) <= 2e-4 * float(want.abs().max())   # cuBLAS vs CPU GEMM in the projections
