@@ -335,3 +335,28 @@ def test_library_was_the_thing_that_ran():
     feats, K, Rt, xs, ys, img = _rig_case(1, 2, 8, (12, 16), (10, 20), seed=1)
     _run(feats, K, Rt, xs, ys, img, "mean", True)
     assert _lib.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("variant", [0, 7])
+def test_mean_division_is_ieee(variant):
+    """mean = sum / V must be the IEEE quotient for every accumulator value: the 3-op exact division in
+    the kernels is checked against true division from the denormal range up to near FLT_MAX, and with
+    +-Inf / NaN accumulators (which must take the guarded library-division path)."""
+    feats, K, Rt, xs, ys, img = _rig_case(1, 7, 16, (34, 60), (30, 90), seed=21)
+    V = torch.tensor(7.0, device=DEV)
+    for scale in (2.0 ** -140, 2.0 ** -126, 2.0 ** -110, 2.0 ** -60, 1.0, 2.0 ** 60, 2.0 ** 120):
+        f = (feats.astype(np.float64) * scale).astype(np.float32)
+        s = _run(f, K, Rt, xs, ys, img, "sum", True, variant=variant)
+        m = _run(f, K, Rt, xs, ys, img, "mean", True, variant=variant)
+        assert torch.equal(m, s / V), scale
+        assert float(s.abs().max()) > 0
+    f = feats.copy()
+    f[0, :, 3, 10:20, 10:30] = np.inf
+    f[0, :, 5, 5:9, 40:50] = -np.inf
+    f[0, :, 7, 20:25, 20:25] = np.nan
+    s = _run(f, K, Rt, xs, ys, img, "sum", True, variant=variant)
+    m = _run(f, K, Rt, xs, ys, img, "mean", True, variant=variant)
+    want = s / V
+    assert torch.equal(torch.isnan(m), torch.isnan(want))
+    assert torch.equal(m[~torch.isnan(m)], want[~torch.isnan(want)])
+    assert bool(torch.isinf(m).any()) and bool(torch.isnan(m).any())

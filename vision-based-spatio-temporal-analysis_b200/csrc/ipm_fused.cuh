@@ -96,14 +96,31 @@ __device__ __forceinline__ void store_pairs(TOut* dst, const float2 (&f)[P]) {
 }
 
 // x / V, correctly rounded, in three FMA-pipe ops instead of the ~10-instruction IEEE division
-// sequence: q = RN(x * r), e = x - q * V (exact in one fma), result = RN(q + e * r) with
-// r = RN(1/V).  This is Markstein's correction step and returns the IEEE quotient whenever no
-// intermediate underflows; tiny |x| (and zeros) take the library division.
-__device__ __forceinline__ float div_exact(float x, float Vf, float r) {
-    if (fabsf(x) < 1e-30f) return __fdiv_rn(x, Vf);
-    const float q = __fmul_rn(x, r);
-    const float e = __fmaf_rn(-q, Vf, x);
-    return __fmaf_rn(e, r, q);
+// sequence: q = RN(x * r), e = x - q * V (exact in one fma, denormals included: flush-to-zero is off),
+// result = RN(q + e * r) with r = RN(1/V) -- Markstein's correction step, which returns the IEEE
+// quotient for every finite x (checked on the device against true division from denormals to
+// FLT_MAX, tests/test_gpu_parity.py::test_mean_division_is_ieee).  +-Inf would turn into NaN
+// (Inf - Inf), so a vector with any non-finite element takes the library division.
+template <int P>
+__device__ __forceinline__ void div_exact_vec(float2 (&a)[P], float Vf, float r) {
+    float mag = 0.0f;
+#pragma unroll
+    for (int e = 0; e < P; ++e) mag = __fadd_rn(__fadd_rn(mag, fabsf(a[e].x)), fabsf(a[e].y));
+    if (mag <= 3.402823466e+38f) {  // every element finite and the sum did not overflow
+        const float2 r2 = make_float2(r, r), nV = make_float2(-Vf, -Vf);
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            const float2 q = __fmul2_rn(a[e], r2);
+            const float2 rem = __ffma2_rn(q, nV, a[e]);
+            a[e] = __ffma2_rn(rem, r2, q);
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < P; ++e) {
+            a[e].x = __fdiv_rn(a[e].x, Vf);
+            a[e].y = __fdiv_rn(a[e].y, Vf);
+        }
+    }
 }
 
 // ---- phase A: project the patch ------------------------------------------------------------
@@ -379,13 +396,8 @@ __global__ void __launch_bounds__(256, MINB) warp_fuse_nhwc_kernel(const FwdPara
 #pragma unroll
                 for (int n = 0; n < NV; ++n) {
                     if (!cok[n]) continue;
-                    if (KMODE == KM_ACC && p.mode == 1 /* BEVIPM_MEAN: sum / V, IEEE quotient */) {
-#pragma unroll
-                        for (int e = 0; e < P; ++e) {
-                            acc[q][n][e].x = div_exact(acc[q][n][e].x, Vf, p.rcpV);
-                            acc[q][n][e].y = div_exact(acc[q][n][e].y, Vf, p.rcpV);
-                        }
-                    }
+                    if (KMODE == KM_ACC && p.mode == 1 /* BEVIPM_MEAN: sum / V, IEEE quotient */)
+                        div_exact_vec<P>(acc[q][n], Vf, p.rcpV);
                     store_pairs<TOut, P>(oc + cvec[n], acc[q][n]);
                 }
             }

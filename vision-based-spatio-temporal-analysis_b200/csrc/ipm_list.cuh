@@ -97,17 +97,16 @@ __device__ __forceinline__ void walk_steps(const FwdParams& p, const StepRec* st
             TOut* oc = orow + (long long)(m & 0xff) * p.os_x;
 #pragma unroll
             for (int nn = 0; nn < NV; ++nn) {
+                if constexpr (KMODE == KM_MAX) {
+                    if (m & 0x200) {  // fusion.py:22: the zeros of views that miss the cell take part
 #pragma unroll
-                for (int e = 0; e < P; ++e) {
-                    if constexpr (KMODE == KM_MAX) {
-                        if (m & 0x200) {  // fusion.py:22: the zeros of views that miss the cell take part
+                        for (int e = 0; e < P; ++e) {
                             acc[nn][e].x = (0.0f > acc[nn][e].x) ? 0.0f : acc[nn][e].x;
                             acc[nn][e].y = (0.0f > acc[nn][e].y) ? 0.0f : acc[nn][e].y;
                         }
-                    } else if (p.mode == 1) {
-                        acc[nn][e].x = div_exact(acc[nn][e].x, Vf, p.rcpV);
-                        acc[nn][e].y = div_exact(acc[nn][e].y, Vf, p.rcpV);
                     }
+                } else if (p.mode == 1) {
+                    div_exact_vec<P>(acc[nn], Vf, p.rcpV);  // BEVIPM_MEAN: sum / V, IEEE quotient
                 }
                 if (cok[nn]) store_pairs<TOut, P>(oc + cvec[nn], acc[nn]);
 #pragma unroll
