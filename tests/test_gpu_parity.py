@@ -122,6 +122,59 @@ def test_variants_bf16_ragged(variant, out_bf16):
         assert _same(out.numpy(), want.numpy())
 
 
+RUN_VARIANTS = list(range(30, 40))   # run kernel: {cells per segment, warps per segment, min CTAs/SM}
+
+
+@pytest.mark.parametrize("variant", RUN_VARIANTS)
+@pytest.mark.parametrize("mode", ["mean", "sum"])
+def test_run_variants_fp32_ragged(variant, mode):
+    # Hb, Wb not multiples of any segment; C = 256: two whole 512-byte chunks (what the run kernel needs)
+    feats, K, Rt, xs, ys, img = _rig_case(2, 7, 256, (31, 53), (37, 91), seed=2)
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, mode)
+    out = _run(feats, K, Rt, xs, ys, img, mode, True, variant=variant).cpu().numpy()
+    assert _same(out, want)
+
+
+@pytest.mark.parametrize("variant", RUN_VARIANTS)
+@pytest.mark.parametrize("out_bf16", [False, True])
+def test_run_variants_bf16_ragged(variant, out_bf16):
+    feats, K, Rt, xs, ys, img = _rig_case(2, 5, 768, (31, 53), (37, 91), seed=4)   # three bf16 chunks
+    fb = torch.from_numpy(feats).bfloat16()
+    want = torch.from_numpy(orc.warp_fuse(fb.float().numpy(), K, Rt, xs, ys, img, "mean"))
+    out = _run(fb.float().numpy(), K, Rt, xs, ys, img, "mean", True, dtype=torch.bfloat16, out_bf16=out_bf16,
+               variant=variant).cpu()
+    if out_bf16:
+        assert torch.equal(out, want.bfloat16())
+    else:
+        assert _same(out.numpy(), want.numpy())
+
+
+@pytest.mark.parametrize("variant", [30, 33, 35, 37])
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_run_kernel_on_golden_geometry(golden, case, variant):
+    """The reference goldens' calibration (views out of frame, cells behind a camera, the |w| guard,
+    non-finite sample positions) with the features tiled up to one whole channel chunk: channel c of
+    the result must equal channel c % C0 of the oracle's."""
+    z = golden(case)
+    feats, K, Rt = _bcast(z)
+    C0 = feats.shape[2]
+    reps = -(-128 // C0)
+    tiled = np.ascontiguousarray(np.tile(feats, (1, 1, reps, 1, 1))[:, :, :128])
+    want = orc.warp_fuse(tiled, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]), "mean")
+    out = _run(tiled, K, Rt, z["xs"], z["ys"], z["img_size"], "mean", True, variant=variant).cpu().numpy()
+    assert _same(out, want)
+    assert _same(out[:, :C0], orc.warp_fuse(feats, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]), "mean"))
+
+
+@pytest.mark.parametrize("views", [1, 2, 9, 16])
+def test_run_kernel_view_counts(views):
+    feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")
+    for variant in (30, 33, 35):
+        out = _run(feats, K, Rt, xs, ys, img, "mean", True, variant=variant).cpu().numpy()
+        assert _same(out, want), variant
+
+
 @pytest.mark.parametrize("mode", ["max", "none"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_max_and_per_view_fast_path(mode, dtype):

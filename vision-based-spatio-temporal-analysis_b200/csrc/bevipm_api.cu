@@ -5,11 +5,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/bevipm.h"
 #include "ipm_aux.cuh"
 #include "ipm_fused.cuh"
 #include "ipm_list.cuh"
+#include "ipm_run.cuh"
 #include "deform_attn.cuh"
 
 namespace {
@@ -91,6 +93,9 @@ constexpr Variant kVariants[] = {
     {4, 2, 2, 0},
     {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0},  // 15..19 unused
     {4, 4, 2, 1}, {4, 4, 3, 1}, {2, 4, 3, 1}, {2, 4, 4, 1}, {1, 4, 6, 1}, {2, 8, 2, 1}, {4, 8, 1, 1}, {1, 4, 4, 1},  // 20..27: list kernel {NV, warps, minb}
+    {0, 0, 0, 0}, {0, 0, 0, 0},                                                                                      // 28, 29 unused
+    {8, 4, 3, 2}, {8, 4, 4, 2}, {8, 2, 3, 2}, {8, 1, 3, 2}, {8, 1, 4, 2}, {16, 1, 3, 2}, {16, 2, 3, 2}, {16, 4, 2, 2},  // 30..37: run kernel {cells, ksplit, minb} (+ ring depth, .ca/.cg: see dispatch_fused)
+    {8, 2, 4, 2}, {16, 4, 3, 2},                                                                                        // 38, 39
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kTH = 8;
@@ -142,6 +147,47 @@ int launch_list(FwdParams p, cudaStream_t st) {
     return 0;
 }
 
+// ---- run kernel (view-major walk, 2x2 blocks re-used in registers) ------------------------------------
+template <typename TIn>
+bool run_kernel_ok(const FwdParams& p) {
+    constexpr int VE = bevipm::VecTraits<TIn>::VE;
+    if (p.mode != BEVIPM_SUM && p.mode != BEVIPM_MEAN) return false;
+    if (p.V > bevipm::kRunMaxViews) return false;
+    if (p.C % (32 * VE)) return false;  // whole 512-byte channel chunks only
+    return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
+}
+
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA>
+int launch_run(FwdParams p, cudaStream_t st) {
+    constexpr int VE = bevipm::VecTraits<TIn>::VE;
+    constexpr int R = NW / KSPLIT;
+    if (!run_kernel_ok<TIn>(p))
+        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs sum/mean, V <= %d, C a multiple of %d, 32-bit tap offsets",
+                    bevipm::kRunMaxViews, 32 * VE);
+    p.tiles_x = ceil_div(p.Wb, CELLS);
+    p.tiles_y = ceil_div(p.Hb, R);
+    p.fsy16 = (int)(p.fs_y / VE);
+    p.fsx16 = (int)(p.fs_x / VE);
+    p.rcpV = 1.0f / (float)p.V;
+    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA>;
+    const size_t smem = (size_t)R * bevipm::run_seg_bytes(p.V, CELLS) + (size_t)NW * DEPTH * 2048;
+    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
+    // at least ~16 CTA waves so the tail stays small
+    int fpc = 1;
+    {
+        const long long tiles = (long long)p.tiles_x * p.tiles_y;
+        const long long slots = 148LL * (65536 / (MAXREG * 32 * NW));
+        while (fpc < 8 && fpc * 2 <= p.B && tiles * ceil_div(p.B, fpc * 2) >= 16 * slots) fpc *= 2;
+        if (const char* e = getenv("BEVIPM_RUN_FPC")) fpc = std::max(1, std::min(atoi(e), p.B));
+    }
+    dim3 grid(p.tiles_x * p.tiles_y, 1, ceil_div(p.B, fpc));
+    kern<<<grid, NW * 32, smem, st>>>(p, fpc);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 template <typename TIn, typename TOut>
 int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st);
@@ -176,6 +222,16 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 25: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 8, 2>(p, st);
         case 26: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 8, 1>(p, st);
         case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
+        case 30: return launch_run<TIn, TOut, 8, 4, 4, 168, 0, false>(p, st);
+        case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
+        case 32: return launch_run<TIn, TOut, 8, 4, 4, 128, 3, false>(p, st);
+        case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
+        case 34: return launch_run<TIn, TOut, 8, 2, 2, 128, 4, false>(p, st);
+        case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
+        case 36: return launch_run<TIn, TOut, 8, 4, 4, 128, 2, false>(p, st);
+        case 37: return launch_run<TIn, TOut, 8, 4, 4, 128, 6, false>(p, st);
+        case 38: return launch_run<TIn, TOut, 16, 4, 1, 168, 4, false>(p, st);
+        case 39: return launch_run<TIn, TOut, 8, 4, 4, 168, 8, false>(p, st);
         case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes
         case 12: return launch_fused<TIn, TOut, 2, 2, bevipm::KM_PROBE, 2, false>(p, st);
         case 13: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_PROBE, 2, false>(p, st);

@@ -1,0 +1,349 @@
+// ipm_run.cuh -- "run" form of the fused warp-and-fuse kernel: taps are re-used in registers.
+//
+// Same arithmetic as ipm_list.cuh / ipm_fused.cuh (geometry.py:120-162 + fusion.py:17-22 of the
+// reference), other walking order.  ncu on the list kernel (profiles/r01_notes.md) showed the two
+// scarce units to be the L1 request path (4 taps x texel bytes per cell-view, 6.3x the HBM bytes) and
+// the issue slots (bf16: 32 of the 56 instructions of a vector-visit only unpack taps).  Walking a BEV
+// row, consecutive cells of one view fall into the SAME 2x2 texel block 1.76x (BASELINE config 1) to
+// 2.4x (config 2) on average (tools/reuse_stats.py), so this kernel walks VIEW-major and keeps the
+// unpacked block in registers for as long as the row stays inside it:
+//
+//   phase A (whole CTA): thread = (row segment, view, cell); project once, mark the cell-views some
+//            view sees and, among them, the ones that START a new 2x2 block ("reloads": the cell
+//            before is not seen or sits in another block).  Two tables per row segment go to shared
+//            memory: per-(view, cell) blend weights, and the compact LOAD LIST (tap offsets of every
+//            reload, in walking order: views ascending, cells ascending).
+//   phase B (per warp = row segment x 512-byte channel chunk): accumulators of all CELLS cells live
+//            in registers; for each view that sees the segment, for each cell (unrolled, so the
+//            accumulator index is static): on a reload bit, unpack the block that is in flight into
+//            the `cur` registers and request the NEXT entry of the load list into the raw registers
+//            just freed (one batch outstanding, flying during the blends up to the next reload);
+//            then blend `cur` with the cell's weights and add to the cell's accumulator.  Per cell
+//            the views are still added in ascending order: the reference's accumulation order.
+//   A tap outside the map gets weight 0 and the address of one of the block's in-map taps (exactly +0
+//   for finite features, as in the list kernel).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ipm_fused.cuh"
+
+namespace bevipm {
+
+constexpr int kRunMaxViews = 16;
+
+// shared-memory bytes of one row segment
+__host__ __device__ constexpr int run_seg_bytes(int V, int cells) {
+    return V * cells * 16                    // blend weights (nw, ne, sw, se) of every (view, cell)
+           + V * cells * 16                  // tap offsets of every (view, cell), un-compacted
+           + (V * cells + 8) * 16            // the load list (+8: entries the walk reads ahead but never copies)
+           + ((V * 8 + 8 + 15) / 16) * 16;   // per-view masks, compact view list, two totals
+}
+
+// ---- async-copy ring helpers (DEPTH > 0) ------------------------------------------------------------
+template <bool CA>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    if constexpr (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    else asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ uint4 lds16(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int4 lds16i(uint32_t addr) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ int lds4i(uint32_t addr) {
+    int v;
+    asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds16f(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// lane base + 16 * off as ONE mad.wide (the base is made opaque so ptxas keeps it in a register pair
+// instead of rebuilding it from blockIdx / threadIdx at every use)
+__device__ __forceinline__ const uint4* tap_ptr(unsigned long long base, int off16) {
+    unsigned long long a;
+    asm("mad.wide.s32 %0, %1, 16, %2;" : "=l"(a) : "r"(off16), "l"(base));
+    return reinterpret_cast<const uint4*>(a);
+}
+// the four taps of one load-list entry -> one ring stage (tap t at +512 t), 16 bytes per lane each
+template <bool CA>
+__device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long base, const int4& o) {
+    cp_async16<CA>(stage, tap_ptr(base, o.x));
+    cp_async16<CA>(stage + 512, tap_ptr(base, o.y));
+    cp_async16<CA>(stage + 1024, tap_ptr(base, o.z));
+    cp_async16<CA>(stage + 1536, tap_ptr(base, o.w));
+}
+
+// DEPTH = 0: the next 2x2 block waits in registers (one batch in flight per warp).  DEPTH = 2, 4, 8: a
+// per-warp ring of DEPTH 2-KB stages in shared memory filled by cp.async (.ca when CA, else .cg), DEPTH-1
+// blocks in flight per warp; every lane reads back exactly the 16 bytes it copied, so no barrier is involved.
+// One CTA walks `fpc` consecutive frames of its tile and re-uses the phase A tables for as long as the
+// calibration of the next frame equals (bit for bit) the one the tables were built from -- static cameras,
+// the normal case (wildtrack_loader.py:291-293 reads one calibration per camera).
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA>
+__global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
+    static_assert(DEPTH == 0 || (DEPTH >= 2 && DEPTH <= 8), "ring depth");
+    using VT = VecTraits<TIn>;
+    constexpr int VE = VT::VE, P = VT::P;
+    constexpr int R = NW / KSPLIT;  // row segments per CTA
+    constexpr int CSH = (CELLS == 16) ? 4 : 3;
+    constexpr unsigned CMASK = (1u << CELLS) - 1u;
+    constexpr int NT = NW * 32;
+    constexpr int ILP = (MAXREG <= 128 && P > 2) ? 2 : P;  // at 128 registers there is room for two chains in flight, not four
+    static_assert(CELLS == 8 || CELLS == 16, "cells per segment");
+    static_assert(NW % KSPLIT == 0 && (KSPLIT == 1 || KSPLIT == 2 || KSPLIT == 4), "warps per row segment");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+
+    const int V = p.V;
+    const int seg_bytes = run_seg_bytes(V, CELLS);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // tells the compiler it is warp-uniform
+    const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
+    const int i0 = ty * R, j0 = tx * CELLS;
+    const int b0 = blockIdx.z * fpc, b1 = min(p.B, b0 + fpc);
+
+    auto seg_wts = [&](int r) { return reinterpret_cast<float4*>(smem_raw + r * seg_bytes); };
+    auto seg_offs = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 16); };
+    auto seg_loads = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 32); };
+    auto seg_meta = [&](int r) { return reinterpret_cast<int*>(smem_raw + r * seg_bytes + V * CELLS * 32 + (V * CELLS + 8) * 16); };
+    // meta: [0, V) per-view mask (seen | reload << 16), [V, 2V) the views that see the segment, [2V] their
+    // number, [2V+1] entries of the load list
+
+    const int total = R * V * CELLS;
+    const int fsv16 = (int)(p.fs_v / VE);
+    const int r = warp / KSPLIT, kk = warp - r * KSPLIT;
+    const int i = i0 + r;
+    const int chunks = p.C / (32 * VE);
+    const float Vf = (float)V;
+    const uint32_t s_wts = (uint32_t)__cvta_generic_to_shared(seg_wts(r));
+    const uint32_t s_loads = (uint32_t)__cvta_generic_to_shared(seg_loads(r));
+    const uint32_t s_meta = (uint32_t)__cvta_generic_to_shared(seg_meta(r));
+    // DEPTH > 0: this lane's 16 bytes of stage 0 / tap 0 in the warp's ring (stage = 2 KB, tap = 512 B)
+    uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + R * seg_bytes + warp * (DEPTH * 2048) + lane * 16;
+    asm volatile("" : "+r"(ring));  // opaque: one register, not re-derived from %tid at every reload
+
+    for (int b = b0; b < b1; ++b) {
+        // ---- same calibration as the frame before? then the tables in shared memory still hold -------------
+        bool rebuild = b == b0;
+        if (b > b0) {
+            bool differs = false;
+            for (int e = tid; e < 21 * V; e += NT) {
+                const float* cur = e < 9 * V ? p.K + (size_t)b * 9 * V + e : p.Rt + (size_t)b * 12 * V + (e - 9 * V);
+                const float* prv = e < 9 * V ? cur - 9 * V : cur - 12 * V;
+                differs |= __float_as_uint(__ldg(cur)) != __float_as_uint(__ldg(prv));
+            }
+            rebuild = __syncthreads_or(differs);  // also: every warp is done with the previous frame's tables
+        }
+        if (rebuild) {
+            // ---- phase A, step 1: project every (segment, view, cell) once ------------------------------------
+            for (int base = warp * 32; base < total; base += NT) {
+                const int e = base + lane;
+                const bool active = e < total;
+                const int g = e >> CSH, c = e & (CELLS - 1);
+                const int rr = g / V, v = g - rr * V;
+                const int ii = i0 + rr, j = j0 + c;
+                CellTap t;
+                t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
+                if (active && ii < p.Hb && j < p.Wb) {
+                    float H[9], ix, iy;
+                    homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
+                    cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + ii), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
+                    t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
+                }
+                const bool seen = t.flags != 0;
+                const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
+                const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
+                const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
+                const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
+                const bool reload = seen && !same;
+                const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
+                if (active) {
+                    const int shift = lane & ~(CELLS - 1);
+                    const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
+                    const int vo = v * fsv16;
+                    const bool nf = (t.flags & kNonFinite) != 0;
+                    const float qnan = __int_as_float(0x7fc00000);
+                    const int tm = t.flags & kTapMask;
+                    const int first = tm ? (__ffs(tm) - 1) : 0;
+                    // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
+                    const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
+                    const float w[4] = {t.nw, t.ne, t.sw, t.se};
+                    int off[4];
+                    float ww[4];
+#pragma unroll
+                    for (int tap = 0; tap < 4; ++tap) {
+                        const bool ok = (tm >> tap) & 1;
+                        off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : safe;
+                        ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
+                    }
+                    seg_wts(rr)[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+                    seg_offs(rr)[v * CELLS + c] = make_int4(off[0], off[1], off[2], off[3]);
+                    if (c == 0) seg_meta(rr)[v] = (int)(seen_c | (reload_c << 16));
+                }
+            }
+            __syncthreads();
+
+            // ---- phase A, step 2: compact the reloads into the load list, the seen views into the view list ----
+            for (int e = tid; e < total; e += NT) {
+                const int g = e >> CSH, c = e & (CELLS - 1);
+                const int rr = g / V, v = g - rr * V;
+                int* ml = seg_meta(rr);
+                const unsigned m = (unsigned)ml[v];
+                const unsigned seen_c = m & 0xffffu, reload_c = m >> 16;
+                const bool is_reload = (reload_c >> c) & 1u;
+                const bool lead = c == 0;
+                if (!is_reload && !lead) continue;
+                int before_loads = 0, before_views = 0, all_loads = 0, all_views = 0;
+                for (int u = 0; u < V; ++u) {
+                    const unsigned mu = (unsigned)ml[u];
+                    const int nl = __popc(mu >> 16), nv = (mu & 0xffffu) ? 1 : 0;
+                    all_loads += nl; all_views += nv;
+                    if (u < v) { before_loads += nl; before_views += nv; }
+                }
+                if (is_reload) {
+                    const int pos = before_loads + __popc(reload_c & ((1u << c) - 1u));
+                    seg_loads(rr)[pos] = seg_offs(rr)[v * CELLS + c];
+                }
+                if (lead) {
+                    if (seen_c) ml[V + before_views] = v;
+                    if (v == 0) {
+                        ml[2 * V] = all_views; ml[2 * V + 1] = all_loads;
+                        for (int z = 0; z < 8; ++z) seg_loads(rr)[all_loads + z] = make_int4(-1, 0, 0, 0);  // end of list
+                    }
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- phase B: per warp, one row segment x one 512-byte channel chunk at a time ---------------------
+        if (i >= p.Hb) continue;
+        const int nviews = __shfl_sync(0xffffffffu, lds4i(s_meta + 8 * V), 0);
+        const int nloads = __shfl_sync(0xffffffffu, lds4i(s_meta + 8 * V + 4), 0);
+        const TIn* fb = reinterpret_cast<const TIn*>(p.feats) + (long long)b * p.fs_b;
+        TOut* orow = reinterpret_cast<TOut*>(p.out) + (long long)b * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x;
+
+        for (int k = kk; k < chunks; k += KSPLIT) {
+            unsigned long long lbase = reinterpret_cast<unsigned long long>(reinterpret_cast<const uint4*>(fb) + (k * 32 + lane));
+            asm volatile("" : "+l"(lbase));  // opaque: stays in its register pair
+            float2 acc[CELLS][P];
+#pragma unroll
+            for (int c = 0; c < CELLS; ++c)
+#pragma unroll
+                for (int q = 0; q < P; ++q) acc[c][q] = make_float2(0.0f, 0.0f);
+
+            if (nviews > 0) {
+                uint4 nxt[4];
+                float2 cur[4][P];
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap)
+#pragma unroll
+                    for (int q = 0; q < P; ++q) cur[tap][q] = make_float2(0.0f, 0.0f);
+                // `lp`: the load-list entry the next reload hands to the copy engine (DEPTH > 0) / requests (0)
+                // (past the end of the list the entries carry x = -1: nothing is copied)
+                uint32_t lp;
+                int4 o;
+                uint32_t st_rd = ring, st_wr = ring + (DEPTH > 0 ? (DEPTH - 1) * 2048 : 0);
+                if constexpr (DEPTH == 0) {
+                    o = lds16i(s_loads);
+                    nxt[0] = ldg16(tap_ptr(lbase, o.x)); nxt[1] = ldg16(tap_ptr(lbase, o.y));
+                    nxt[2] = ldg16(tap_ptr(lbase, o.z)); nxt[3] = ldg16(tap_ptr(lbase, o.w));
+                    lp = s_loads + 16;
+                } else {
+                    // entries 0 .. DEPTH-2 start flying now; one commit group per entry, empty past the list's end
+#pragma unroll
+                    for (int s = 0; s < DEPTH - 1; ++s) {
+                        if (s < nloads) {
+                            o = lds16i(s_loads + s * 16);
+                            run_copy4<CA>(ring + s * 2048, lbase, o);
+                        }
+                        cp_async_commit();
+                    }
+                    lp = s_loads + (DEPTH - 1) * 16;
+                }
+                for (int vi = 0; vi < nviews; ++vi) {
+                    const int v = lds4i(s_meta + 4 * (V + vi));
+                    const unsigned m = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_meta + 4 * v), 0);  // warp-uniform
+                    const uint32_t wv = s_wts + v * (CELLS * 16);
+                    float4 wn = lds16f(wv);
+                    // A cell the view does not see is never a reload; its blend runs on whatever `cur` holds
+                    // and is simply not added (predicated), so the only branch per cell is "reload?".
+                    bool rl = (m >> 16) & 1u;
+#pragma unroll
+                    for (int c = 0; c < CELLS; ++c) {
+                        const float4 w = wn;
+                        if (c + 1 < CELLS) wn = lds16f(wv + (c + 1) * 16);  // one cell ahead of its use
+                        const bool seen = (m >> c) & 1u;                       // warp-uniform
+                        const bool rl_now = rl;
+                        if (c + 1 < CELLS) rl = (m >> (17 + c)) & 1u;          // decided one cell early
+                        if (rl_now) {                                          // the row leaves the block held in `cur`
+                            if constexpr (DEPTH == 0) {
+#pragma unroll
+                                for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
+                                const int4 o = lds16i(lp);
+                                if (o.x >= 0) {
+                                    nxt[0] = ldg16(tap_ptr(lbase, o.x)); nxt[1] = ldg16(tap_ptr(lbase, o.y));
+                                    nxt[2] = ldg16(tap_ptr(lbase, o.z)); nxt[3] = ldg16(tap_ptr(lbase, o.w));
+                                }
+                            } else {
+                                cp_async_wait<DEPTH - 2>();  // the oldest entry has landed (a lane reads back its own bytes)
+                                nxt[0] = lds16(st_rd); nxt[1] = lds16(st_rd + 512);
+                                nxt[2] = lds16(st_rd + 1024); nxt[3] = lds16(st_rd + 1536);
+                                const int4 o = lds16i(lp);
+#pragma unroll
+                                for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
+                                // the entry DEPTH-1 ahead goes into the stage unpacked at the previous reload
+                                if (o.x >= 0) run_copy4<CA>(st_wr, lbase, o);
+                                cp_async_commit();
+                                st_wr = st_rd;
+                                st_rd = (st_rd == ring + (DEPTH - 1) * 2048) ? ring : st_rd + 2048;
+                            }
+                            lp += 16;
+                        }
+                        // out_v = fma(SE,se, fma(SW,sw, fma(NE,ne, NW*nw)))   ATen's interpolation order; ILP of
+                        // the P independent chains are written interleaved so an instruction does not wait
+                        // on the one right before it
+#pragma unroll
+                        for (int q0 = 0; q0 < P; q0 += ILP) {
+                            float2 sv[ILP];
+#pragma unroll
+                            for (int q = 0; q < ILP; ++q) sv[q] = __fmul2_rn(cur[0][q0 + q], make_float2(w.x, w.x));
+#pragma unroll
+                            for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[1][q0 + q], make_float2(w.y, w.y), sv[q]);
+#pragma unroll
+                            for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[2][q0 + q], make_float2(w.z, w.z), sv[q]);
+#pragma unroll
+                            for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
+#pragma unroll
+                            for (int q = 0; q < ILP; ++q)
+                                if (seen) acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
+                        }
+                    }
+                }
+                if constexpr (DEPTH > 0) cp_async_wait<0>();  // (only empty groups are left) the ring restarts per chunk
+            }
+
+            const int cvec = (k * 32 + lane) * VE;
+#pragma unroll
+            for (int c = 0; c < CELLS; ++c) {
+                if (j0 + c < p.Wb) {
+                    if (p.mode == 1) div_exact_vec<P>(acc[c], Vf, p.rcpV);  // BEVIPM_MEAN: sum / V, IEEE quotient
+                    store_pairs<TOut, P>(orow + (long long)c * p.os_x + cvec, acc[c]);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace bevipm
