@@ -9,7 +9,7 @@ import ctypes
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libbevipm.so"
+LIB_PATH = Path(__import__("os").environ.get("BEVIPM_LIB", PKG / "libbevipm.so"))  # BEVIPM_LIB: A/B of two builds (development aid)
 
 F32, BF16 = 0, 1
 SUM, MEAN, MAX, NONE = 0, 1, 2, 3

@@ -96,6 +96,7 @@ constexpr Variant kVariants[] = {
     {0, 0, 0, 0}, {0, 0, 0, 0},                                                                                      // 28, 29 unused
     {8, 4, 3, 2}, {8, 4, 4, 2}, {8, 2, 3, 2}, {8, 1, 3, 2}, {8, 1, 4, 2}, {16, 1, 3, 2}, {16, 2, 3, 2}, {16, 4, 2, 2},  // 30..37: run kernel {cells, ksplit, minb} (+ ring depth, .ca/.cg: see dispatch_fused)
     {8, 2, 4, 2}, {16, 4, 3, 2},                                                                                        // 38, 39
+    {8, 4, 4, 3}, {8, 4, 4, 3},                                                                                         // 40, 41: run-kernel timing probes
 };
 constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
 constexpr int kTH = 8;
@@ -157,7 +158,7 @@ bool run_kernel_ok(const FwdParams& p) {
     return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
 }
 
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA>
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0>
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
@@ -169,7 +170,7 @@ int launch_run(FwdParams p, cudaStream_t st) {
     p.fsy16 = (int)(p.fs_y / VE);
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
-    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA>;
+    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE>;
     const size_t smem = (size_t)R * bevipm::run_seg_bytes(p.V, CELLS) + (size_t)NW * DEPTH * 2048;
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
@@ -193,14 +194,19 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st);
     if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
     if (variant == 0) {
-        // Default = the list kernel, with as many 16-byte vectors per lane as one texel holds (up to 4):
-        // measured best on every BASELINE shape (profiles/r01_notes.md): texel 2 KB (c1, c2) -> NV 4,
-        // 512 B (c3) -> NV 1.  Feature maps too large for its 32-bit offsets fall back to the tile kernel.
+        // Defaults, measured on every BASELINE shape (profiles/r01_notes.md):
+        //  * fp32 features, whole 512-byte channel chunks, sum/mean: the run kernel (taps re-used in registers
+        //    along the row), one warp per row segment walking all chunks -- 4 % (c1) to 7 % (c3) ahead of the list kernel;
+        //  * otherwise the list kernel with as many 16-byte vectors per lane as one texel holds (up to 4): texel
+        //    2 KB (c2) -> NV 4, 512 B -> NV 1.  bf16 spends 32 of its ~60 instructions per cell-view unpacking, the
+        //    two kernels tie there (0.78 ms on c2) and the list kernel stays.
+        //  Feature maps too large for 32-bit tap offsets fall back to the tile kernel.
         const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
         const long long span = (long long)p.V * (p.fs_v / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
         if (span > 0x7fffffffLL) variant = 7;
+        else if (sizeof(TIn) == 4 && run_kernel_ok<TIn>(p)) variant = 33;
         else variant = texel_bytes >= 2048 ? 21 : (texel_bytes >= 1024 ? 23 : 27);
     }
     switch (variant) {
@@ -222,16 +228,18 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 25: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 8, 2>(p, st);
         case 26: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 8, 1>(p, st);
         case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
-        case 30: return launch_run<TIn, TOut, 8, 4, 4, 168, 0, false>(p, st);
+        case 30: return launch_run<TIn, TOut, 8, 4, 4, 128, 5, false>(p, st);
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
-        case 32: return launch_run<TIn, TOut, 8, 4, 4, 128, 3, false>(p, st);
+        case 32: return launch_run<TIn, TOut, 6, 4, 4, 128, 4, false>(p, st);
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
         case 34: return launch_run<TIn, TOut, 8, 2, 2, 128, 4, false>(p, st);
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
-        case 36: return launch_run<TIn, TOut, 8, 4, 4, 128, 2, false>(p, st);
-        case 37: return launch_run<TIn, TOut, 8, 4, 4, 128, 6, false>(p, st);
+        case 36: return launch_run<TIn, TOut, 6, 4, 4, 128, 6, false>(p, st);
+        case 37: return launch_run<TIn, TOut, 6, 4, 1, 128, 4, false>(p, st);
         case 38: return launch_run<TIn, TOut, 16, 4, 1, 168, 4, false>(p, st);
-        case 39: return launch_run<TIn, TOut, 8, 4, 4, 168, 8, false>(p, st);
+        case 39: return launch_run<TIn, TOut, 4, 4, 4, 96, 4, false>(p, st);
+        case 40: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 1>(p, st);  // timing probes (not the fusion)
+        case 41: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 2>(p, st);
         case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes
         case 12: return launch_fused<TIn, TOut, 2, 2, bevipm::KM_PROBE, 2, false>(p, st);
         case 13: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_PROBE, 2, false>(p, st);

@@ -86,23 +86,24 @@ __device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long bas
     cp_async16<CA>(stage + 1536, tap_ptr(base, o.w));
 }
 
-// DEPTH = 0: the next 2x2 block waits in registers (one batch in flight per warp).  DEPTH = 2, 4, 8: a
-// per-warp ring of DEPTH 2-KB stages in shared memory filled by cp.async (.ca when CA, else .cg), DEPTH-1
+// A per-warp ring of DEPTH 2-KB stages in shared memory is filled by cp.async (.ca when CA, else .cg), DEPTH-1
 // blocks in flight per warp; every lane reads back exactly the 16 bytes it copied, so no barrier is involved.
 // One CTA walks `fpc` consecutive frames of its tile and re-uses the phase A tables for as long as the
 // calibration of the next frame equals (bit for bit) the one the tables were built from -- static cameras,
 // the normal case (wildtrack_loader.py:291-293 reads one calibration per camera).
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA>
+// PROBE (timing aid, results are NOT the fusion): 1 = no copies are issued (instruction side alone), 2 = copies and
+// unpack but no blend (memory side alone)
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0>
 __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
-    static_assert(DEPTH == 0 || (DEPTH >= 2 && DEPTH <= 8), "ring depth");
+    static_assert(DEPTH >= 2 && DEPTH <= 8, "ring depth");
     using VT = VecTraits<TIn>;
     constexpr int VE = VT::VE, P = VT::P;
     constexpr int R = NW / KSPLIT;  // row segments per CTA
-    constexpr int CSH = (CELLS == 16) ? 4 : 3;
+    constexpr int GPW = 32 / CELLS;  // (segment, view) groups one warp projects per pass: a group = CELLS adjacent lanes
     constexpr unsigned CMASK = (1u << CELLS) - 1u;
     constexpr int NT = NW * 32;
-    constexpr int ILP = (MAXREG <= 128 && P > 2) ? 2 : P;  // at 128 registers there is room for two chains in flight, not four
-    static_assert(CELLS == 8 || CELLS == 16, "cells per segment");
+    constexpr int ILP = (MAXREG <= 128 && P > 2 && CELLS >= 8) ? 2 : P;  // at 128 registers there is room for two chains in flight, not four
+    static_assert(CELLS >= 2 && CELLS <= 16, "cells per segment");
     static_assert(NW % KSPLIT == 0 && (KSPLIT == 1 || KSPLIT == 2 || KSPLIT == 4), "warps per row segment");
     extern __shared__ __align__(16) unsigned char smem_raw[];
 
@@ -134,109 +135,109 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + R * seg_bytes + warp * (DEPTH * 2048) + lane * 16;
     asm volatile("" : "+r"(ring));  // opaque: one register, not re-derived from %tid at every reload
 
-    for (int b = b0; b < b1; ++b) {
-        // ---- same calibration as the frame before? then the tables in shared memory still hold -------------
-        bool rebuild = b == b0;
-        if (b > b0) {
+    const int cpw = (chunks - kk + KSPLIT - 1) / KSPLIT;  // 512-byte chunks this warp walks per frame
+
+    for (int b = b0; b < b1;) {
+        if (b > b0) __syncthreads();  // every warp is done with the previous run's tables
+        // ---- phase A, step 1: project every (segment, view, cell) once ------------------------------------
+        for (int gbase = warp * GPW; gbase < R * V; gbase += NW * GPW) {
+            const int gl = lane / CELLS, c = lane - gl * CELLS;
+            const int g = gbase + gl;
+            const bool active = gl < GPW && g < R * V;
+            const int rr = g / V, v = g - rr * V;
+            const int ii = i0 + rr, j = j0 + c;
+            CellTap t;
+            t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
+            if (active && ii < p.Hb && j < p.Wb) {
+                float H[9], ix, iy;
+                homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
+                cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + ii), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
+                t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
+            }
+            const bool seen = t.flags != 0;
+            const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
+            const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
+            const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
+            const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
+            const bool reload = seen && !same;
+            const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
+            if (active) {
+                const int shift = gl * CELLS;
+                const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
+                const int vo = v * fsv16;
+                const bool nf = (t.flags & kNonFinite) != 0;
+                const float qnan = __int_as_float(0x7fc00000);
+                const int tm = t.flags & kTapMask;
+                const int first = tm ? (__ffs(tm) - 1) : 0;
+                // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
+                const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
+                const float w[4] = {t.nw, t.ne, t.sw, t.se};
+                int off[4];
+                float ww[4];
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const bool ok = (tm >> tap) & 1;
+                    off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : safe;
+                    ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
+                }
+                seg_wts(rr)[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+                seg_offs(rr)[v * CELLS + c] = make_int4(off[0], off[1], off[2], off[3]);
+                if (c == 0) seg_meta(rr)[v] = (int)(seen_c | (reload_c << 16));
+            }
+        }
+        __syncthreads();
+
+        // ---- phase A, step 2: compact the reloads into the load list, the seen views into the view list ----
+        for (int e = tid; e < total; e += NT) {
+            const int g = e / CELLS, c = e - g * CELLS;
+            const int rr = g / V, v = g - rr * V;
+            int* ml = seg_meta(rr);
+            const unsigned m = (unsigned)ml[v];
+            const unsigned seen_c = m & 0xffffu, reload_c = m >> 16;
+            const bool is_reload = (reload_c >> c) & 1u;
+            const bool lead = c == 0;
+            if (!is_reload && !lead) continue;
+            int before_loads = 0, before_views = 0, all_loads = 0, all_views = 0;
+            for (int u = 0; u < V; ++u) {
+                const unsigned mu = (unsigned)ml[u];
+                const int nl = __popc(mu >> 16), nv = (mu & 0xffffu) ? 1 : 0;
+                all_loads += nl; all_views += nv;
+                if (u < v) { before_loads += nl; before_views += nv; }
+            }
+            if (is_reload) {
+                const int pos = before_loads + __popc(reload_c & ((1u << c) - 1u));
+                seg_loads(rr)[pos] = seg_offs(rr)[v * CELLS + c];
+            }
+            if (lead) {
+                if (seen_c) ml[V + before_views] = v;
+                if (v == 0) {
+                    ml[2 * V] = all_views; ml[2 * V + 1] = all_loads;
+                    for (int z = 0; z < 8; ++z) seg_loads(rr)[all_loads + z] = make_int4(-1, 0, 0, 0);  // end of list
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- the run of frames b .. e-1 shares these tables: same calibration, bit for bit -----------------------
+        int e = b + 1;
+        for (; e < b1; ++e) {
             bool differs = false;
-            for (int e = tid; e < 21 * V; e += NT) {
-                const float* cur = e < 9 * V ? p.K + (size_t)b * 9 * V + e : p.Rt + (size_t)b * 12 * V + (e - 9 * V);
-                const float* prv = e < 9 * V ? cur - 9 * V : cur - 12 * V;
+            for (int z = tid; z < 21 * V; z += NT) {
+                const float* cur = z < 9 * V ? p.K + (size_t)e * 9 * V + z : p.Rt + (size_t)e * 12 * V + (z - 9 * V);
+                const float* prv = z < 9 * V ? cur - 9 * V : cur - 12 * V;
                 differs |= __float_as_uint(__ldg(cur)) != __float_as_uint(__ldg(prv));
             }
-            rebuild = __syncthreads_or(differs);  // also: every warp is done with the previous frame's tables
+            if (__syncthreads_or(differs)) break;
         }
-        if (rebuild) {
-            // ---- phase A, step 1: project every (segment, view, cell) once ------------------------------------
-            for (int base = warp * 32; base < total; base += NT) {
-                const int e = base + lane;
-                const bool active = e < total;
-                const int g = e >> CSH, c = e & (CELLS - 1);
-                const int rr = g / V, v = g - rr * V;
-                const int ii = i0 + rr, j = j0 + c;
-                CellTap t;
-                t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
-                if (active && ii < p.Hb && j < p.Wb) {
-                    float H[9], ix, iy;
-                    homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
-                    cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + ii), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
-                    t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
-                }
-                const bool seen = t.flags != 0;
-                const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
-                const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
-                const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
-                const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
-                const bool reload = seen && !same;
-                const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
-                if (active) {
-                    const int shift = lane & ~(CELLS - 1);
-                    const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
-                    const int vo = v * fsv16;
-                    const bool nf = (t.flags & kNonFinite) != 0;
-                    const float qnan = __int_as_float(0x7fc00000);
-                    const int tm = t.flags & kTapMask;
-                    const int first = tm ? (__ffs(tm) - 1) : 0;
-                    // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
-                    const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
-                    const float w[4] = {t.nw, t.ne, t.sw, t.se};
-                    int off[4];
-                    float ww[4];
-#pragma unroll
-                    for (int tap = 0; tap < 4; ++tap) {
-                        const bool ok = (tm >> tap) & 1;
-                        off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : safe;
-                        ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
-                    }
-                    seg_wts(rr)[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
-                    seg_offs(rr)[v * CELLS + c] = make_int4(off[0], off[1], off[2], off[3]);
-                    if (c == 0) seg_meta(rr)[v] = (int)(seen_c | (reload_c << 16));
-                }
-            }
-            __syncthreads();
+        const int b_run = b;
+        const int n_items = (e - b) * cpw;  // this warp's (frame, chunk) items, frame-major
+        b = e;
 
-            // ---- phase A, step 2: compact the reloads into the load list, the seen views into the view list ----
-            for (int e = tid; e < total; e += NT) {
-                const int g = e >> CSH, c = e & (CELLS - 1);
-                const int rr = g / V, v = g - rr * V;
-                int* ml = seg_meta(rr);
-                const unsigned m = (unsigned)ml[v];
-                const unsigned seen_c = m & 0xffffu, reload_c = m >> 16;
-                const bool is_reload = (reload_c >> c) & 1u;
-                const bool lead = c == 0;
-                if (!is_reload && !lead) continue;
-                int before_loads = 0, before_views = 0, all_loads = 0, all_views = 0;
-                for (int u = 0; u < V; ++u) {
-                    const unsigned mu = (unsigned)ml[u];
-                    const int nl = __popc(mu >> 16), nv = (mu & 0xffffu) ? 1 : 0;
-                    all_loads += nl; all_views += nv;
-                    if (u < v) { before_loads += nl; before_views += nv; }
-                }
-                if (is_reload) {
-                    const int pos = before_loads + __popc(reload_c & ((1u << c) - 1u));
-                    seg_loads(rr)[pos] = seg_offs(rr)[v * CELLS + c];
-                }
-                if (lead) {
-                    if (seen_c) ml[V + before_views] = v;
-                    if (v == 0) {
-                        ml[2 * V] = all_views; ml[2 * V + 1] = all_loads;
-                        for (int z = 0; z < 8; ++z) seg_loads(rr)[all_loads + z] = make_int4(-1, 0, 0, 0);  // end of list
-                    }
-                }
-            }
-            __syncthreads();
-        }
-
-        // ---- phase B: per warp, one row segment x one 512-byte channel chunk at a time ---------------------
-        if (i >= p.Hb) continue;
+        // ---- phase B: per warp, one row segment x one 512-byte channel chunk of one frame at a time ----------
+        if (i >= p.Hb || n_items <= 0) continue;
         const int nviews = __shfl_sync(0xffffffffu, lds4i(s_meta + 8 * V), 0);
-        const int nloads = __shfl_sync(0xffffffffu, lds4i(s_meta + 8 * V + 4), 0);
-        const TIn* fb = reinterpret_cast<const TIn*>(p.feats) + (long long)b * p.fs_b;
-        TOut* orow = reinterpret_cast<TOut*>(p.out) + (long long)b * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x;
-
-        for (int k = kk; k < chunks; k += KSPLIT) {
-            unsigned long long lbase = reinterpret_cast<unsigned long long>(reinterpret_cast<const uint4*>(fb) + (k * 32 + lane));
-            asm volatile("" : "+l"(lbase));  // opaque: stays in its register pair
+        int fi_c = 0, k_c = kk;  // frame (within the run) and chunk of the item being blended
+        for (int it = 0; it < n_items; ++it) {
             float2 acc[CELLS][P];
 #pragma unroll
             for (int c = 0; c < CELLS; ++c)
@@ -244,34 +245,25 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 for (int q = 0; q < P; ++q) acc[c][q] = make_float2(0.0f, 0.0f);
 
             if (nviews > 0) {
-                uint4 nxt[4];
                 float2 cur[4][P];
 #pragma unroll
                 for (int tap = 0; tap < 4; ++tap)
 #pragma unroll
                     for (int q = 0; q < P; ++q) cur[tap][q] = make_float2(0.0f, 0.0f);
-                // `lp`: the load-list entry the next reload hands to the copy engine (DEPTH > 0) / requests (0)
-                // (past the end of the list the entries carry x = -1: nothing is copied)
-                uint32_t lp;
-                int4 o;
-                uint32_t st_rd = ring, st_wr = ring + (DEPTH > 0 ? (DEPTH - 1) * 2048 : 0);
-                if constexpr (DEPTH == 0) {
-                    o = lds16i(s_loads);
-                    nxt[0] = ldg16(tap_ptr(lbase, o.x)); nxt[1] = ldg16(tap_ptr(lbase, o.y));
-                    nxt[2] = ldg16(tap_ptr(lbase, o.z)); nxt[3] = ldg16(tap_ptr(lbase, o.w));
-                    lp = s_loads + 16;
-                } else {
-                    // entries 0 .. DEPTH-2 start flying now; one commit group per entry, empty past the list's end
+                // lane base of this item's chunk; opaque so it stays in its register pair
+                unsigned long long lbase = reinterpret_cast<unsigned long long>(
+                    reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(p.feats) + (long long)(b_run + fi_c) * p.fs_b) + (k_c * 32 + lane));
+                asm volatile("" : "+l"(lbase));
+                // entries 0 .. DEPTH-2 of the load list start flying now: one commit group per entry (past the
+                // end of the list the entries carry x = -1: nothing is copied, the group is empty)
+                uint32_t st_rd = ring, st_wr = ring + (DEPTH - 1) * 2048;
 #pragma unroll
-                    for (int s = 0; s < DEPTH - 1; ++s) {
-                        if (s < nloads) {
-                            o = lds16i(s_loads + s * 16);
-                            run_copy4<CA>(ring + s * 2048, lbase, o);
-                        }
-                        cp_async_commit();
-                    }
-                    lp = s_loads + (DEPTH - 1) * 16;
+                for (int s = 0; s < DEPTH - 1; ++s) {
+                    const int4 o = lds16i(s_loads + s * 16);
+                    if (PROBE != 1 && o.x >= 0) run_copy4<CA>(ring + s * 2048, lbase, o);
+                    cp_async_commit();
                 }
+                uint32_t lp = s_loads + (DEPTH - 1) * 16;  // the entry the next reload hands to the copy engine
                 for (int vi = 0; vi < nviews; ++vi) {
                     const int v = lds4i(s_meta + 4 * (V + vi));
                     const unsigned m = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_meta + 4 * v), 0);  // warp-uniform
@@ -288,58 +280,106 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                         const bool rl_now = rl;
                         if (c + 1 < CELLS) rl = (m >> (17 + c)) & 1u;          // decided one cell early
                         if (rl_now) {                                          // the row leaves the block held in `cur`
-                            if constexpr (DEPTH == 0) {
+                            cp_async_wait<DEPTH - 2>();  // the oldest entry has landed (a lane reads back its own bytes)
+                            uint4 nxt[4];
+                            nxt[0] = lds16(st_rd); nxt[1] = lds16(st_rd + 512);
+                            nxt[2] = lds16(st_rd + 1024); nxt[3] = lds16(st_rd + 1536);
+                            const int4 o = lds16i(lp);
 #pragma unroll
-                                for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
-                                const int4 o = lds16i(lp);
-                                if (o.x >= 0) {
-                                    nxt[0] = ldg16(tap_ptr(lbase, o.x)); nxt[1] = ldg16(tap_ptr(lbase, o.y));
-                                    nxt[2] = ldg16(tap_ptr(lbase, o.z)); nxt[3] = ldg16(tap_ptr(lbase, o.w));
-                                }
-                            } else {
-                                cp_async_wait<DEPTH - 2>();  // the oldest entry has landed (a lane reads back its own bytes)
-                                nxt[0] = lds16(st_rd); nxt[1] = lds16(st_rd + 512);
-                                nxt[2] = lds16(st_rd + 1024); nxt[3] = lds16(st_rd + 1536);
-                                const int4 o = lds16i(lp);
-#pragma unroll
-                                for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
-                                // the entry DEPTH-1 ahead goes into the stage unpacked at the previous reload
-                                if (o.x >= 0) run_copy4<CA>(st_wr, lbase, o);
-                                cp_async_commit();
-                                st_wr = st_rd;
-                                st_rd = (st_rd == ring + (DEPTH - 1) * 2048) ? ring : st_rd + 2048;
-                            }
+                            for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
+                            // the entry DEPTH-1 ahead goes into the stage unpacked at the previous reload
+                            if (PROBE != 1 && o.x >= 0) run_copy4<CA>(st_wr, lbase, o);
+                            cp_async_commit();
                             lp += 16;
+                            st_wr = st_rd;
+                            st_rd = (st_rd == ring + (DEPTH - 1) * 2048) ? ring : st_rd + 2048;
                         }
-                        // out_v = fma(SE,se, fma(SW,sw, fma(NE,ne, NW*nw)))   ATen's interpolation order; ILP of
-                        // the P independent chains are written interleaved so an instruction does not wait
-                        // on the one right before it
+                        if constexpr (PROBE == 2) {
+                            if (rl_now) {
 #pragma unroll
-                        for (int q0 = 0; q0 < P; q0 += ILP) {
-                            float2 sv[ILP];
+                                for (int q = 0; q < P; ++q) {
+                                    acc[c][q].x = __uint_as_float(__float_as_uint(acc[c][q].x) ^ __float_as_uint(cur[0][q].x) ^ __float_as_uint(cur[1][q].y));
+                                    acc[c][q].y = __uint_as_float(__float_as_uint(acc[c][q].y) ^ __float_as_uint(cur[2][q].x) ^ __float_as_uint(cur[3][q].y));
+                                }
+                            }
+                        } else {
+                            // out_v = fma(SE,se, fma(SW,sw, fma(NE,ne, NW*nw)))   ATen's interpolation order; ILP of
+                            // the P independent chains are written interleaved so an instruction does not wait
+                            // on the one right before it
 #pragma unroll
-                            for (int q = 0; q < ILP; ++q) sv[q] = __fmul2_rn(cur[0][q0 + q], make_float2(w.x, w.x));
+                            for (int q0 = 0; q0 < P; q0 += ILP) {
+                                float2 sv[ILP];
 #pragma unroll
-                            for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[1][q0 + q], make_float2(w.y, w.y), sv[q]);
+                                for (int q = 0; q < ILP; ++q) sv[q] = __fmul2_rn(cur[0][q0 + q], make_float2(w.x, w.x));
 #pragma unroll
-                            for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[2][q0 + q], make_float2(w.z, w.z), sv[q]);
+                                for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[1][q0 + q], make_float2(w.y, w.y), sv[q]);
 #pragma unroll
-                            for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
+                                for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[2][q0 + q], make_float2(w.z, w.z), sv[q]);
 #pragma unroll
-                            for (int q = 0; q < ILP; ++q)
-                                if (seen) acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
+                                for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
+#pragma unroll
+                                for (int q = 0; q < ILP; ++q)
+                                    if (seen) acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
+                            }
                         }
                     }
                 }
-                if constexpr (DEPTH > 0) cp_async_wait<0>();  // (only empty groups are left) the ring restarts per chunk
+                cp_async_wait<0>();  // (only empty groups are left) the ring restarts with the next item
             }
 
-            const int cvec = (k * 32 + lane) * VE;
+            // ---- epilogue: mean division (IEEE quotient) and one 16-byte store per cell ---------------------------
+            if (p.mode == 1) {
+                // Markstein's 3-op division is exact for finite sums (ipm_fused.cuh div_exact_vec); +-Inf would
+                // turn into NaN.  One test per chunk: the packed sum of all CELLS x 8 accumulators is finite
+                // only if every one of them is (Inf - Inf = NaN; a finite overflow merely takes the slow path).
+                float2 t[CELLS];
 #pragma unroll
-            for (int c = 0; c < CELLS; ++c) {
-                if (j0 + c < p.Wb) {
-                    if (p.mode == 1) div_exact_vec<P>(acc[c], Vf, p.rcpV);  // BEVIPM_MEAN: sum / V, IEEE quotient
-                    store_pairs<TOut, P>(orow + (long long)c * p.os_x + cvec, acc[c]);
+                for (int c = 0; c < CELLS; ++c) {
+                    float2 u = acc[c][0];
+#pragma unroll
+                    for (int q = 1; q < P; ++q) u = __fadd2_rn(u, acc[c][q]);
+                    t[c] = u;
+                }
+#pragma unroll
+                for (int w = 1; w < CELLS; w *= 2)
+#pragma unroll
+                    for (int c = 0; c + w < CELLS; c += 2 * w) t[c] = __fadd2_rn(t[c], t[c + w]);
+                const float tot = __fadd_rn(t[0].x, t[0].y);
+                if (fabsf(tot) <= 3.402823466e+38f) {
+                    const float r = p.rcpV;
+#pragma unroll
+                    for (int c = 0; c < CELLS; ++c)
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            const float2 qq = __fmul2_rn(acc[c][q], make_float2(r, r));
+                            const float2 rem = __ffma2_rn(qq, make_float2(-Vf, -Vf), acc[c][q]);
+                            acc[c][q] = __ffma2_rn(rem, make_float2(r, r), qq);
+                        }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < CELLS; ++c)
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            acc[c][q].x = __fdiv_rn(acc[c][q].x, Vf);
+                            acc[c][q].y = __fdiv_rn(acc[c][q].y, Vf);
+                        }
+                }
+            }
+            TOut* oc = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_c) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
+                       (k_c * 32 + lane) * VE;
+            k_c += KSPLIT;
+            if (k_c >= chunks) { k_c = kk; ++fi_c; }
+            if (j0 + CELLS <= p.Wb) {
+#pragma unroll
+                for (int c = 0; c < CELLS; ++c) {
+                    store_pairs<TOut, P>(oc, acc[c]);
+                    oc += p.os_x;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < CELLS; ++c) {
+                    if (j0 + c < p.Wb) store_pairs<TOut, P>(oc, acc[c]);
+                    oc += p.os_x;
                 }
             }
         }
