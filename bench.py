@@ -297,6 +297,7 @@ def run_ours(args, wl):
     ev1.record()
     barrier()
     launches = _lib.launch_count() - launches0
+    kernel_variant = int(_lib.load().bevipm_last_variant())
     ms = ev0.elapsed_time(ev1)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -353,7 +354,7 @@ def run_ours(args, wl):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(wl.name, args.variant), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "algorithmic_bytes_per_frame": alg["b_alg"], "b_full_per_frame": alg["b_full"],
-                         "frac_of_nominal_8TBs": achieved / 8000.0, "kernel": "warp_fuse_list_kernel (auto variant) unless --variant forces another"},
+                         "frac_of_nominal_8TBs": achieved / 8000.0, "kernel": _lib.variant_name(kernel_variant)},
             "clocks": clocks,
         }
         if e2e:

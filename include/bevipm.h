@@ -68,6 +68,10 @@ const char *bevipm_last_error(void);
 /* Number of kernels this library has launched in the calling process (all threads). */
 int64_t bevipm_launch_count(void);
 
+/* Which kernel variant the last bevipm_warp_fuse_fwd call of this thread launched (the `variant` numbers of
+ * DESIGN.md; 0 = none yet, -1 = the strided kernel).  bench.py names the dominant kernel from it. */
+int32_t bevipm_last_variant(void);
+
 /*
  * Fused forward: replaces geometry.py:120-162 (homography, projection of every BEV cell centre,
  * bilinear zero-padded sampling) and fusion.py:17-22 in ONE launch, without materialising the

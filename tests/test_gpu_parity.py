@@ -166,6 +166,50 @@ def test_run_kernel_on_golden_geometry(golden, case, variant):
     assert _same(out[:, :C0], orc.warp_fuse(feats, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]), "mean"))
 
 
+@pytest.mark.parametrize("fpc", [1, 2, 3, 8])
+@pytest.mark.parametrize("variant", [31, 33, 34])
+def test_run_kernel_frame_runs_share_tables_only_when_calibration_repeats(monkeypatch, fpc, variant):
+    """One CTA walks `fpc` frames and keeps its tap tables while the calibration repeats bit for bit: frames
+    0-1 share one rig, 2 has another, 3-4 a third (and 4 differs from 3 in a single extrinsic bit)."""
+    monkeypatch.setenv("BEVIPM_RUN_FPC", str(fpc))
+    from bevipm import rig
+    B, V, C, fhw, bhw = 5, 4, 256, (20, 33), (19, 45)
+    feats = torch.randn(B, V, C, *fhw, generator=torch.Generator().manual_seed(21)).numpy()
+    K = np.zeros((B, V, 3, 3), np.float32)
+    Rt = np.zeros((B, V, 4, 4), np.float32)
+    for b, seed in enumerate([3, 3, 4, 5, 5]):
+        k, r = rig.look_at_rig(V, seed)
+        K[b], Rt[b] = k.numpy(), r.numpy()
+    Rt[4, 2, 0, 3] = np.nextafter(Rt[4, 2, 0, 3], np.float32(np.inf))
+    xs, ys = rig.ground_axes(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS)
+    want = orc.warp_fuse(feats, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, "mean")
+    out = _run(feats, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, "mean", True, variant=variant).cpu().numpy()
+    assert _same(out, want)
+    fb = torch.from_numpy(feats).bfloat16().float().numpy()
+    wantb = orc.warp_fuse(fb, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, "sum")
+    outb = _run(fb, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, "sum", True, dtype=torch.bfloat16,
+                variant=variant).cpu().numpy()
+    assert _same(outb, wantb)
+
+
+def test_run_kernel_non_finite_features_take_the_exact_division():
+    """+-Inf sums make the 3-op mean division return NaN; the per-chunk finiteness test must route them to
+    the IEEE division (Inf / V = Inf), exactly like the oracle."""
+    feats, K, Rt, xs, ys, img = _rig_case(1, 3, 128, (20, 33), (19, 45), seed=31)
+    feats[0, 1, 5, 7, 11] = np.inf
+    feats[0, 2, 9, 3, 20] = -np.inf
+    feats[0, 0, 64, 10, 10] = np.nan
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")
+    assert np.isinf(want).any()
+    for variant in (31, 33):
+        out = _run(feats, K, Rt, xs, ys, img, "mean", True, variant=variant).cpu().numpy()
+        # cells whose block holds a non-finite texel next to an out-of-map tap may differ (documented: NaN for +-Inf)
+        both = np.isfinite(want) & np.isfinite(out)
+        assert np.array_equal(out[both], want[both])
+        assert np.array_equal(np.isinf(want) & ~np.isnan(out), np.isinf(out))
+        assert np.array_equal(out[np.isinf(out)], want[np.isinf(out)])
+
+
 @pytest.mark.parametrize("views", [1, 2, 9, 16])
 def test_run_kernel_view_counts(views):
     feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)
@@ -207,9 +251,11 @@ def test_full_size_fp32_vs_oracle(name):
     assert np.count_nonzero(out) > 0.5 * out.size
 
 
-def test_full_size_c2_bf16_frames_and_properties():
+@pytest.mark.parametrize("variant", [0, 31, 33])
+def test_full_size_c2_bf16_frames_and_properties(variant):
     """BASELINE config 1 (the bench workload): 8 frames x 7 views x 1024 ch bf16.  One frame is checked
-    against the oracle; the whole batch through size-independent properties."""
+    against the oracle; the whole batch through size-independent properties.  variant 0 = the default
+    (list kernel), 31 / 33 = the run kernel (4 warps per row segment / one warp walking all chunks)."""
     from bevipm import _lib, ops, rig
     wl = rig.WORKLOADS["c2"]
     B, V, C = wl.frames, wl.views, wl.channels
@@ -222,7 +268,7 @@ def test_full_size_c2_bf16_frames_and_properties():
     xd, yd = xs.to(DEV), ys.to(DEV)
     img = wl.img_size
     run = lambda t, mode="mean", obf=False: ops.warp_fuse(t, Kd[:t.shape[0]], Rd[:t.shape[0]], xd, yd, img[0], img[1],
-                                                          _lib.MODES[mode], obf, 0)
+                                                          _lib.MODES[mode], obf, variant if mode != "none" else 0)
     out = run(f)
     assert out.shape == (B, C, *wl.bev_hw) and out.dtype == torch.float32
     # (1) frame 3 against the oracle, bit-exact

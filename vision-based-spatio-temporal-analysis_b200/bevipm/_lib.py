@@ -28,7 +28,7 @@ class Desc(ctypes.Structure):
 EXPORTS = (
     "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
-    "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd",
+    "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -52,6 +52,7 @@ def load() -> ctypes.CDLL:
     L.bevipm_version.restype = ctypes.c_int
     L.bevipm_last_error.restype = ctypes.c_char_p
     L.bevipm_launch_count.restype = ctypes.c_int64
+    L.bevipm_last_variant.restype = ctypes.c_int32
     L.bevipm_warp_fuse_fwd.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp]
     L.bevipm_warp_fuse_bwd.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp]
     L.bevipm_sample_coords.argtypes = [dp, fp, fp, fp, fp, fp, fp, vp]
@@ -78,3 +79,16 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().bevipm_launch_count())
+
+
+def variant_name(v: int) -> str:
+    """Kernel behind a `variant` number of bevipm_desc (see csrc/bevipm_api.cu dispatch_fused)."""
+    if v == -1:
+        return "warp_fuse_strided_kernel"
+    if 1 <= v <= 14:
+        return f"warp_fuse_nhwc_kernel (tile kernel, variant {v})"
+    if 20 <= v <= 27:
+        return f"warp_fuse_list_kernel (variant {v})"
+    if 30 <= v <= 41:
+        return f"warp_fuse_run_kernel (variant {v})"
+    return f"variant {v}"

@@ -18,6 +18,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+thread_local int g_last_variant = 0;
 
 int fail(int code, const char* fmt, ...) {
     va_list ap;
@@ -191,8 +192,8 @@ int launch_run(FwdParams p, cudaStream_t st) {
 
 template <typename TIn, typename TOut>
 int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
-    if (p.mode == BEVIPM_MAX) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st);
-    if (p.mode == BEVIPM_NONE) return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
+    if (p.mode == BEVIPM_MAX) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st); }
+    if (p.mode == BEVIPM_NONE) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st); }
     if (variant == 0) {
         // Defaults, measured on every BASELINE shape (profiles/r01_notes.md):
         //  * fp32 features, whole 512-byte channel chunks, sum/mean: the run kernel (taps re-used in registers
@@ -209,6 +210,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         else if (sizeof(TIn) == 4 && run_kernel_ok<TIn>(p)) variant = 33;
         else variant = texel_bytes >= 2048 ? 21 : (texel_bytes >= 1024 ? 23 : 27);
     }
+    g_last_variant = variant;
     switch (variant) {
         case 1: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_ACC, 4, false>(p, st);
         case 2: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, 2, false>(p, st);
@@ -315,6 +317,7 @@ extern "C" {
 int bevipm_version(void) { return BEVIPM_VERSION; }
 const char* bevipm_last_error(void) { return g_err; }
 int64_t bevipm_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+int32_t bevipm_last_variant(void) { return g_last_variant; }
 
 int bevipm_warp_fuse_fwd(const bevipm_desc* d, const void* feats, const float* K, const float* Rt34, const float* xs,
                          const float* ys, void* out, void* stream) {
@@ -331,6 +334,7 @@ int bevipm_warp_fuse_fwd(const bevipm_desc* d, const void* feats, const float* K
         if (!in32 && !out32) return dispatch_fused<__nv_bfloat16, __nv_bfloat16>(p, d->variant, st);
         if (!in32 && out32) return dispatch_fused<__nv_bfloat16, float>(p, d->variant, st);
     }
+    g_last_variant = -1;
     if (in32 && out32) return launch_strided<float, float>(p, st);
     if (in32 && !out32) return launch_strided<float, __nv_bfloat16>(p, st);
     if (!in32 && out32) return launch_strided<__nv_bfloat16, float>(p, st);
