@@ -207,7 +207,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
                                (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
         if (span > 0x7fffffffLL) variant = 7;
-        else if (sizeof(TIn) == 4 && run_kernel_ok<TIn>(p)) variant = 33;
+        else if (sizeof(TIn) == 4 && run_kernel_ok<TIn>(p)) variant = 32;
         else variant = texel_bytes >= 2048 ? 21 : (texel_bytes >= 1024 ? 23 : 27);
     }
     g_last_variant = variant;
@@ -232,14 +232,14 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
         case 30: return launch_run<TIn, TOut, 8, 4, 4, 128, 5, false>(p, st);
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
-        case 32: return launch_run<TIn, TOut, 6, 4, 4, 128, 4, false>(p, st);
+        case 32: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
         case 34: return launch_run<TIn, TOut, 8, 2, 2, 128, 4, false>(p, st);
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
-        case 36: return launch_run<TIn, TOut, 6, 4, 4, 128, 6, false>(p, st);
-        case 37: return launch_run<TIn, TOut, 6, 4, 1, 128, 4, false>(p, st);
+        case 36: return launch_run<TIn, TOut, 8, 4, 1, 80, 4, false>(p, st);
+        case 37: return launch_run<TIn, TOut, 16, 4, 1, 128, 4, false>(p, st);
         case 38: return launch_run<TIn, TOut, 16, 4, 1, 168, 4, false>(p, st);
-        case 39: return launch_run<TIn, TOut, 4, 4, 4, 96, 4, false>(p, st);
+        case 39: return launch_run<TIn, TOut, 16, 4, 1, 96, 3, false>(p, st);
         case 40: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 1>(p, st);  // timing probes (not the fusion)
         case 41: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 2>(p, st);
         case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes

@@ -36,7 +36,6 @@ constexpr int kRunMaxViews = 16;
 // shared-memory bytes of one row segment
 __host__ __device__ constexpr int run_seg_bytes(int V, int cells) {
     return V * cells * 16                    // blend weights (nw, ne, sw, se) of every (view, cell)
-           + V * cells * 16                  // tap offsets of every (view, cell), un-compacted
            + (V * cells + 8) * 16            // the load list (+8: entries the walk reads ahead but never copies)
            + ((V * 8 + 8 + 15) / 16) * 16;   // per-view masks, compact view list, two totals
 }
@@ -116,13 +115,11 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     const int b0 = blockIdx.z * fpc, b1 = min(p.B, b0 + fpc);
 
     auto seg_wts = [&](int r) { return reinterpret_cast<float4*>(smem_raw + r * seg_bytes); };
-    auto seg_offs = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 16); };
-    auto seg_loads = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 32); };
-    auto seg_meta = [&](int r) { return reinterpret_cast<int*>(smem_raw + r * seg_bytes + V * CELLS * 32 + (V * CELLS + 8) * 16); };
+    auto seg_loads = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 16); };
+    auto seg_meta = [&](int r) { return reinterpret_cast<int*>(smem_raw + r * seg_bytes + V * CELLS * 16 + (V * CELLS + 8) * 16); };
     // meta: [0, V) per-view mask (seen | reload << 16), [V, 2V) the views that see the segment, [2V] their
     // number, [2V+1] entries of the load list
 
-    const int total = R * V * CELLS;
     const int fsv16 = (int)(p.fs_v / VE);
     const int r = warp / KSPLIT, kk = warp - r * KSPLIT;
     const int i = i0 + r;
@@ -139,95 +136,93 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
 
     for (int b = b0; b < b1;) {
         if (b > b0) __syncthreads();  // every warp is done with the previous run's tables
-        // ---- phase A, step 1: project every (segment, view, cell) once ------------------------------------
-        for (int gbase = warp * GPW; gbase < R * V; gbase += NW * GPW) {
+        // ---- phase A: the first warp of every row segment builds the segment's tables, directly in walking order --
+        // lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view
+        // that sees the segment its place in the view list (lane order = views ascending, cells ascending).
+        if (kk == 0) {
+            float4* wts = seg_wts(r);
+            int4* loads = seg_loads(r);
+            int* ml = seg_meta(r);
             const int gl = lane / CELLS, c = lane - gl * CELLS;
-            const int g = gbase + gl;
-            const bool active = gl < GPW && g < R * V;
-            const int rr = g / V, v = g - rr * V;
-            const int ii = i0 + rr, j = j0 + c;
-            CellTap t;
-            t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
-            if (active && ii < p.Hb && j < p.Wb) {
-                float H[9], ix, iy;
-                homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
-                cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + ii), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
-                t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
-            }
-            const bool seen = t.flags != 0;
-            const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
-            const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
-            const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
-            const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
-            const bool reload = seen && !same;
-            const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
-            if (active) {
+            const unsigned lt = (1u << lane) - 1u;
+            int nloads = 0, nseen = 0;  // warp-uniform running totals
+            for (int v0 = 0; v0 < V; v0 += GPW) {
+                const int v = v0 + gl;
+                const bool active = gl < GPW && v < V;
+                const int j = j0 + c;
+                CellTap t;
+                t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
+                if (active && i < p.Hb && j < p.Wb) {
+                    float H[9], ix, iy;
+                    homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
+                    cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
+                    t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
+                }
+                const bool seen = t.flags != 0;
+                const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
+                const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
+                const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
+                const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
+                const bool reload = seen && !same;  // the row enters a new 2x2 block here
+                const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
                 const int shift = gl * CELLS;
                 const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
-                const int vo = v * fsv16;
-                const bool nf = (t.flags & kNonFinite) != 0;
-                const float qnan = __int_as_float(0x7fc00000);
-                const int tm = t.flags & kTapMask;
-                const int first = tm ? (__ffs(tm) - 1) : 0;
-                // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
-                const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
-                const float w[4] = {t.nw, t.ne, t.sw, t.se};
-                int off[4];
-                float ww[4];
+                const bool lead_seen = active && c == 0 && seen_c != 0;
+                const unsigned lead_b = __ballot_sync(0xffffffffu, lead_seen);
+                if (active) {
+                    const int vo = v * fsv16;
+                    const bool nf = (t.flags & kNonFinite) != 0;
+                    const float qnan = __int_as_float(0x7fc00000);
+                    const int tm = t.flags & kTapMask;
+                    const int first = tm ? (__ffs(tm) - 1) : 0;
+                    // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
+                    const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
+                    const float w[4] = {t.nw, t.ne, t.sw, t.se};
+                    int off[4];
+                    float ww[4];
 #pragma unroll
-                for (int tap = 0; tap < 4; ++tap) {
-                    const bool ok = (tm >> tap) & 1;
-                    off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : safe;
-                    ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
+                    for (int tap = 0; tap < 4; ++tap) {
+                        const bool ok = (tm >> tap) & 1;
+                        off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : safe;
+                        ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
+                    }
+                    wts[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+                    if (reload) loads[nloads + __popc(reload_b & lt)] = make_int4(off[0], off[1], off[2], off[3]);
+                    if (c == 0) ml[v] = (int)(seen_c | (reload_c << 16));
+                    if (lead_seen) ml[V + nseen + __popc(lead_b & lt)] = v;
                 }
-                seg_wts(rr)[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
-                seg_offs(rr)[v * CELLS + c] = make_int4(off[0], off[1], off[2], off[3]);
-                if (c == 0) seg_meta(rr)[v] = (int)(seen_c | (reload_c << 16));
+                nloads += __popc(reload_b);
+                nseen += __popc(lead_b);
             }
+            if (lane == 0) { ml[2 * V] = nseen; ml[2 * V + 1] = nloads; }
+            if (lane < 8) loads[nloads + lane] = make_int4(-1, 0, 0, 0);  // end of list
         }
-        __syncthreads();
-
-        // ---- phase A, step 2: compact the reloads into the load list, the seen views into the view list ----
-        for (int e = tid; e < total; e += NT) {
-            const int g = e / CELLS, c = e - g * CELLS;
-            const int rr = g / V, v = g - rr * V;
-            int* ml = seg_meta(rr);
-            const unsigned m = (unsigned)ml[v];
-            const unsigned seen_c = m & 0xffffu, reload_c = m >> 16;
-            const bool is_reload = (reload_c >> c) & 1u;
-            const bool lead = c == 0;
-            if (!is_reload && !lead) continue;
-            int before_loads = 0, before_views = 0, all_loads = 0, all_views = 0;
-            for (int u = 0; u < V; ++u) {
-                const unsigned mu = (unsigned)ml[u];
-                const int nl = __popc(mu >> 16), nv = (mu & 0xffffu) ? 1 : 0;
-                all_loads += nl; all_views += nv;
-                if (u < v) { before_loads += nl; before_views += nv; }
-            }
-            if (is_reload) {
-                const int pos = before_loads + __popc(reload_c & ((1u << c) - 1u));
-                seg_loads(rr)[pos] = seg_offs(rr)[v * CELLS + c];
-            }
-            if (lead) {
-                if (seen_c) ml[V + before_views] = v;
-                if (v == 0) {
-                    ml[2 * V] = all_views; ml[2 * V + 1] = all_loads;
-                    for (int z = 0; z < 8; ++z) seg_loads(rr)[all_loads + z] = make_int4(-1, 0, 0, 0);  // end of list
-                }
-            }
-        }
-        __syncthreads();
+        if (KSPLIT > 1) __syncthreads();
+        else __syncwarp();
 
         // ---- the run of frames b .. e-1 shares these tables: same calibration, bit for bit -----------------------
-        int e = b + 1;
-        for (; e < b1; ++e) {
+        int e = b1;
+        if (b + 1 < b1) {
+            // all comparisons of the group in one round (the loads overlap); the usual answer is "no frame differs"
             bool differs = false;
-            for (int z = tid; z < 21 * V; z += NT) {
-                const float* cur = z < 9 * V ? p.K + (size_t)e * 9 * V + z : p.Rt + (size_t)e * 12 * V + (z - 9 * V);
-                const float* prv = z < 9 * V ? cur - 9 * V : cur - 12 * V;
+            const int per = 21 * V, n = per * (b1 - b - 1);
+            for (int z = tid; z < n; z += NT) {
+                const int f = z / per, q = z - f * per;  // frame b + 1 + f against its predecessor
+                const float* cur = q < 9 * V ? p.K + (size_t)(b + 1 + f) * 9 * V + q : p.Rt + (size_t)(b + 1 + f) * 12 * V + (q - 9 * V);
+                const float* prv = q < 9 * V ? cur - 9 * V : cur - 12 * V;
                 differs |= __float_as_uint(__ldg(cur)) != __float_as_uint(__ldg(prv));
             }
-            if (__syncthreads_or(differs)) break;
+            if (__syncthreads_or(differs)) {
+                for (e = b + 1; e < b1; ++e) {
+                    bool d = false;
+                    for (int q = tid; q < per; q += NT) {
+                        const float* cur = q < 9 * V ? p.K + (size_t)e * 9 * V + q : p.Rt + (size_t)e * 12 * V + (q - 9 * V);
+                        const float* prv = q < 9 * V ? cur - 9 * V : cur - 12 * V;
+                        d |= __float_as_uint(__ldg(cur)) != __float_as_uint(__ldg(prv));
+                    }
+                    if (__syncthreads_or(d)) break;
+                }
+            }
         }
         const int b_run = b;
         const int n_items = (e - b) * cpw;  // this warp's (frame, chunk) items, frame-major
