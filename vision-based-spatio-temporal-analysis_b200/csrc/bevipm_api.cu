@@ -172,7 +172,7 @@ int launch_run(FwdParams p, cudaStream_t st) {
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
     auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE>;
-    const size_t smem = (size_t)R * bevipm::run_seg_bytes(p.V, CELLS) + (size_t)NW * DEPTH * 2048;
+    const size_t smem = (size_t)R * bevipm::run_seg_bytes(p.V, CELLS) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48;  // tables, rings, homographies
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
     // at least ~16 CTA waves so the tail stays small
@@ -196,18 +196,18 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     if (p.mode == BEVIPM_NONE) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st); }
     if (variant == 0) {
         // Defaults, measured on every BASELINE shape (profiles/r01_notes.md):
-        //  * fp32 features, whole 512-byte channel chunks, sum/mean: the run kernel (taps re-used in registers
-        //    along the row), one warp per row segment walking all chunks -- 4 % (c1) to 7 % (c3) ahead of the list kernel;
-        //  * otherwise the list kernel with as many 16-byte vectors per lane as one texel holds (up to 4): texel
-        //    2 KB (c2) -> NV 4, 512 B -> NV 1.  bf16 spends 32 of its ~60 instructions per cell-view unpacking, the
-        //    two kernels tie there (0.78 ms on c2) and the list kernel stays.
+        //  * whole 512-byte channel chunks, sum/mean, V <= 16: the run kernel (taps re-used in registers along the
+        //    row), one warp per row segment walking all chunks; fp32 at 96 registers (20 warps/SM), bf16 at 128
+        //    (the unpacked block needs 32 registers).  c1 0.088 ms, c2 0.76-0.78 ms, c3 0.258 ms against the list
+        //    kernel's 0.098 / 0.78-0.82 / 0.376.
+        //  * otherwise the list kernel with as many 16-byte vectors per lane as one texel holds (up to 4).
         //  Feature maps too large for 32-bit tap offsets fall back to the tile kernel.
         const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
         const long long span = (long long)p.V * (p.fs_v / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
         if (span > 0x7fffffffLL) variant = 7;
-        else if (sizeof(TIn) == 4 && run_kernel_ok<TIn>(p)) variant = 32;
+        else if (run_kernel_ok<TIn>(p)) variant = sizeof(TIn) == 4 ? 32 : 33;
         else variant = texel_bytes >= 2048 ? 21 : (texel_bytes >= 1024 ? 23 : 27);
     }
     g_last_variant = variant;
@@ -236,10 +236,10 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
         case 34: return launch_run<TIn, TOut, 8, 2, 2, 128, 4, false>(p, st);
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
-        case 36: return launch_run<TIn, TOut, 8, 4, 1, 80, 4, false>(p, st);
+        case 36: return launch_run<TIn, TOut, 8, 4, 2, 128, 4, false>(p, st);
         case 37: return launch_run<TIn, TOut, 16, 4, 1, 128, 4, false>(p, st);
         case 38: return launch_run<TIn, TOut, 16, 4, 1, 168, 4, false>(p, st);
-        case 39: return launch_run<TIn, TOut, 16, 4, 1, 96, 3, false>(p, st);
+        case 39: return launch_run<TIn, TOut, 16, 4, 1, 112, 4, false>(p, st);
         case 40: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 1>(p, st);  // timing probes (not the fusion)
         case 41: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 2>(p, st);
         case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes

@@ -136,6 +136,16 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
 
     for (int b = b0; b < b1;) {
         if (b > b0) __syncthreads();  // every warp is done with the previous run's tables
+        // ---- the V homographies of this frame, once per CTA (geometry.py:60-63): rows padded to 4 floats ------------
+        float* sH = reinterpret_cast<float*>(smem_raw + R * seg_bytes + NW * (DEPTH * 2048));
+        if (tid < V) {
+            float H[9];
+            homography(p.K + 9 * (b * V + tid), p.Rt + 12 * (b * V + tid), H);
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                reinterpret_cast<float4*>(sH + 12 * tid)[q] = make_float4(H[3 * q], H[3 * q + 1], H[3 * q + 2], 0.0f);
+        }
+        __syncthreads();
         // ---- phase A: the first warp of every row segment builds the segment's tables, directly in walking order --
         // lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view
         // that sees the segment its place in the view list (lane order = views ascending, cells ascending).
@@ -154,7 +164,9 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
                 if (active && i < p.Hb && j < p.Wb) {
                     float H[9], ix, iy;
-                    homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
+                    const float4* hv = reinterpret_cast<const float4*>(sH + 12 * v);
+                    const float4 h0 = hv[0], h1 = hv[1], h2 = hv[2];
+                    H[0] = h0.x; H[1] = h0.y; H[2] = h0.z; H[3] = h1.x; H[4] = h1.y; H[5] = h1.z; H[6] = h2.x; H[7] = h2.y; H[8] = h2.z;
                     cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
                     t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
                 }
