@@ -161,13 +161,17 @@ def cpu_port_frames_per_s(wl, budget_s: float = 12.0, min_frames: int = 1):
         f = f.bfloat16().float()
     f = f.permute(0, 1, 4, 2, 3).numpy()
     Kn, Rn = K[None].numpy(), Rt[None].numpy()
-    threads = orc.num_threads()
-    orc.warp_fuse(f, Kn, Rn, xs.numpy(), ys.numpy(), wl.img_size, wl.fusion, nthreads=0, channels_last_out=True)  # warm
+    # every host core this process may use (torchrun exports OMP_NUM_THREADS=1: ask for the cores explicitly)
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or orc.num_threads()
+    orc.warp_fuse(f, Kn, Rn, xs.numpy(), ys.numpy(), wl.img_size, wl.fusion, nthreads=threads, channels_last_out=True)  # warm
     times = []
     t_end = time.perf_counter() + budget_s
     while len(times) < min_frames or (time.perf_counter() < t_end and len(times) < 64):
         t0 = time.perf_counter()
-        orc.warp_fuse(f, Kn, Rn, xs.numpy(), ys.numpy(), wl.img_size, wl.fusion, nthreads=0, channels_last_out=True)
+        orc.warp_fuse(f, Kn, Rn, xs.numpy(), ys.numpy(), wl.img_size, wl.fusion, nthreads=threads, channels_last_out=True)
         times.append(time.perf_counter() - t0)
     per_frame = statistics.median(times)
     return {"value": 1.0 / per_frame, "unit": UNIT, "cores": threads, "kind": "port",
@@ -231,7 +235,22 @@ def run_ours(args, wl):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries ONE JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # ... whoever prints it: the communicator is created (and warmed) with fd 1 pointing at stderr
+        sys.stdout.flush()
+        keep = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            w = torch.zeros(1, device=dev)
+            dist.all_reduce(w)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(keep, 1)
+            os.close(keep)
 
     def barrier():
         if world > 1:
