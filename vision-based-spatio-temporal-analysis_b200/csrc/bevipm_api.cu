@@ -192,7 +192,19 @@ int launch_run(FwdParams p, cudaStream_t st) {
 
 template <typename TIn, typename TOut>
 int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
-    if (p.mode == BEVIPM_MAX) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st); }
+    if (p.mode == BEVIPM_MAX) {
+        // max fusion (fusion.py:22): the list kernel's KM_MAX walk (2.5x the tile kernel on config 1); the tile kernel
+        // when the caller forces it (variant 1) or the maps are too large for 32-bit tap offsets
+        const long long span = (long long)p.V * (p.fs_v / bevipm::VecTraits<TIn>::VE) +
+                               (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
+                               (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
+        if (variant == 1 || span > 0x7fffffffLL) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st); }
+        const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
+        if (texel_bytes >= 2048) { g_last_variant = 21; return launch_list<TIn, TOut, 4, bevipm::KM_MAX, 4, 3>(p, st); }
+        if (texel_bytes >= 1024) { g_last_variant = 23; return launch_list<TIn, TOut, 2, bevipm::KM_MAX, 4, 4>(p, st); }
+        g_last_variant = 27;
+        return launch_list<TIn, TOut, 1, bevipm::KM_MAX, 4, 4>(p, st);
+    }
     if (p.mode == BEVIPM_NONE) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st); }
     if (variant == 0) {
         // Defaults, measured on every BASELINE shape (profiles/r01_notes.md):
