@@ -2,9 +2,10 @@
 project/models/fusion/{geometry,fusion}.py).  CUDA only: importing the product path without
 libbevipm.so raises."""
 from . import rig  # host-side synthetic inputs; no GPU needed
-from .modules import (AttentionFusion, ConcatFusion, DeformAttnFusion, FusedIPM, FusionModule, GeometryTransformer, SimpleFusion,
+from .modules import (AttentionFusion, ConcatFusion, DeformAttnFusion, FoldedConcatProjIPM, FusedIPM, FusionModule, GeometryTransformer,
+                      SimpleFusion,
                       pack_calibration)
 from . import ops, sharding
 
-__all__ = ["GeometryTransformer", "FusedIPM", "FusionModule", "SimpleFusion", "ConcatFusion", "AttentionFusion", "DeformAttnFusion",
+__all__ = ["GeometryTransformer", "FusedIPM", "FoldedConcatProjIPM", "FusionModule", "SimpleFusion", "ConcatFusion", "AttentionFusion", "DeformAttnFusion",
            "pack_calibration", "ops", "rig", "sharding"]

@@ -188,6 +188,42 @@ class FusedIPM(_IPMBase):
         return out
 
 
+class FoldedConcatProjIPM(_IPMBase):
+    """GeometryTransformer -> ConcatFusion -> 1x1 projection of BEVNet (model_wrapper.py:68-73) with the
+    projection folded in FRONT of the warp.
+
+    The warp is linear per channel, so  proj(concat_v(warp_v(f_v))) = sum_v warp_v(W_v f_v) + bias  with
+    W_v = proj.weight[:, v*C:(v+1)*C]: the per-view 1x1 convolution runs on the small source maps (one batched
+    GEMM, a library call), the fused SUM kernel then gathers `out_channels` instead of V*C channels per cell and
+    the [B,V*C,Hb,Wb] tensor never exists (7 x 1280 x 120 x 360 fp32 = 1.55 GB per frame at wildtrack.yaml).
+    A reassociation of the reference's arithmetic: equal within fp32 rounding (tests: 1e-4 relative), not bit-exact.
+
+    `proj` is the nn.Conv2d(V*C, out_channels, 1) the reference builds lazily (model_wrapper.py:70-72); it stays
+    the owner of weight and bias, so checkpoints load unchanged and gradients reach it through the GEMM.
+    """
+
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, proj: nn.Conv2d, views: int, variant: int = 0):
+        super().__init__(bev_h, bev_w, bev_bounds)
+        assert proj.kernel_size == (1, 1) and proj.in_channels % views == 0
+        self.proj = proj
+        self.views = views
+        self.variant = variant
+
+    def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
+                img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
+        B, V, C, Hf, Wf = feats.shape
+        assert V == self.views and V * C == self.proj.in_channels
+        Co = self.proj.out_channels
+        W = self.proj.weight.view(Co, V, C).to(torch.float32)                      # [Co,V,C]
+        x = feats.to(torch.float32).permute(0, 1, 3, 4, 2)                        # [B,V,Hf,Wf,C] (view, no copy if channels-last)
+        g = torch.einsum("bvhwc,ovc->bvhwo", x, W)                                 # per-view 1x1 conv, channels-last result
+        g = g.permute(0, 1, 4, 2, 3)                                               # logical [B,V,Co,Hf,Wf], NHWC in memory
+        out = self._run(g, intrinsics, extrinsics, img_size, _lib.SUM, False, self.variant, "keep")
+        if self.proj.bias is not None:
+            out = out + self.proj.bias.view(1, Co, 1, 1)
+        return out
+
+
 class FusionModule(nn.Module):
     def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
         """bev_maps: Tensor[B, V, C, H, W] -> Tensor[B, C, H, W]   (fusion.py:5-8)"""
