@@ -210,6 +210,25 @@ def test_run_kernel_non_finite_features_take_the_exact_division():
         assert np.array_equal(out[np.isinf(out)], want[np.isinf(out)])
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_default_dispatch_random_shapes(seed):
+    """Whatever kernel the library picks (variant 0) for a random shape and mode must equal the oracle: whole and
+    partial channel chunks, 1..17 views, BEV grids smaller and larger than the source maps."""
+    rng = np.random.RandomState(1000 + seed)
+    B, V = int(rng.randint(1, 4)), int(rng.choice([1, 2, 3, 5, 7, 8, 9, 16, 17]))
+    bf16 = bool(rng.randint(0, 2))
+    C = int(rng.choice([256, 512, 264] if bf16 else [128, 256, 384, 132]))
+    fhw = (int(rng.randint(8, 40)), int(rng.randint(8, 60)))
+    bhw = (int(rng.randint(5, 50)), int(rng.randint(5, 100)))
+    mode = str(rng.choice(["mean", "sum", "max"]))
+    feats, K, Rt, xs, ys, img = _rig_case(B, V, C, fhw, bhw, seed=seed)
+    if bf16:
+        feats = torch.from_numpy(feats).bfloat16().float().numpy()
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, mode)
+    out = _run(feats, K, Rt, xs, ys, img, mode, True, dtype=torch.bfloat16 if bf16 else torch.float32).cpu().numpy()
+    assert _same(out, want), (B, V, C, fhw, bhw, mode, bf16)
+
+
 @pytest.mark.parametrize("views", [1, 2, 9, 16])
 def test_run_kernel_view_counts(views):
     feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)

@@ -246,12 +246,12 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
         case 32: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
-        case 34: return launch_run<TIn, TOut, 8, 2, 2, 128, 4, false>(p, st);
+        case 34: return launch_run<TIn, TOut, 8, 4, 1, 128, 5, false>(p, st);
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
-        case 36: return launch_run<TIn, TOut, 8, 4, 2, 128, 4, false>(p, st);
+        case 36: return launch_run<TIn, TOut, 8, 4, 1, 96, 3, false>(p, st);
         case 37: return launch_run<TIn, TOut, 16, 4, 1, 128, 4, false>(p, st);
         case 38: return launch_run<TIn, TOut, 16, 4, 1, 168, 4, false>(p, st);
-        case 39: return launch_run<TIn, TOut, 16, 4, 1, 112, 4, false>(p, st);
+        case 39: return launch_run<TIn, TOut, 8, 4, 1, 128, 6, false>(p, st);
         case 40: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 1>(p, st);  // timing probes (not the fusion)
         case 41: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 2>(p, st);
         case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes

@@ -244,6 +244,24 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
         if (i >= p.Hb || n_items <= 0) continue;
         const int nviews = __shfl_sync(0xffffffffu, lds4i(s_meta + 8 * V), 0);
         int fi_c = 0, k_c = kk;  // frame (within the run) and chunk of the item being blended
+        // lane base of an item's chunk
+        auto item_base = [&](int fi, int k) {
+            return reinterpret_cast<unsigned long long>(
+                reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(p.feats) + (long long)(b_run + fi) * p.fs_b) + (k * 32 + lane));
+        };
+        // entries 0 .. DEPTH-2 of the load list start flying: one commit group per entry (past the end of the list
+        // the entries carry x = -1: nothing is copied, the group is empty).  Called before the first item and, for
+        // every later item, right after the walk of the one before it: the copies fly during that item's epilogue.
+        auto prime = [&](unsigned long long base) {
+#pragma unroll
+            for (int s = 0; s < DEPTH - 1; ++s) {
+                const int4 o = lds16i(s_loads + s * 16);
+                if (PROBE != 1 && o.x >= 0) run_copy4<CA>(ring + s * 2048, base, o);
+                cp_async_commit();
+            }
+        };
+        unsigned long long lbase = item_base(0, kk);
+        if (nviews > 0) prime(lbase);
         for (int it = 0; it < n_items; ++it) {
             float2 acc[CELLS][P];
 #pragma unroll
@@ -257,19 +275,8 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 for (int tap = 0; tap < 4; ++tap)
 #pragma unroll
                     for (int q = 0; q < P; ++q) cur[tap][q] = make_float2(0.0f, 0.0f);
-                // lane base of this item's chunk; opaque so it stays in its register pair
-                unsigned long long lbase = reinterpret_cast<unsigned long long>(
-                    reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(p.feats) + (long long)(b_run + fi_c) * p.fs_b) + (k_c * 32 + lane));
-                asm volatile("" : "+l"(lbase));
-                // entries 0 .. DEPTH-2 of the load list start flying now: one commit group per entry (past the
-                // end of the list the entries carry x = -1: nothing is copied, the group is empty)
+                asm volatile("" : "+l"(lbase));  // opaque: the lane base stays in its register pair
                 uint32_t st_rd = ring, st_wr = ring + (DEPTH - 1) * 2048;
-#pragma unroll
-                for (int s = 0; s < DEPTH - 1; ++s) {
-                    const int4 o = lds16i(s_loads + s * 16);
-                    if (PROBE != 1 && o.x >= 0) run_copy4<CA>(ring + s * 2048, lbase, o);
-                    cp_async_commit();
-                }
                 uint32_t lp = s_loads + (DEPTH - 1) * 16;  // the entry the next reload hands to the copy engine
                 for (int vi = 0; vi < nviews; ++vi) {
                     const int v = lds4i(s_meta + 4 * (V + vi));
@@ -333,6 +340,14 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 }
                 cp_async_wait<0>();  // (only empty groups are left) the ring restarts with the next item
             }
+            // the item after this one: its first blocks fly while this item is divided, packed and stored
+            const int k_this = k_c, fi_this = fi_c;
+            k_c += KSPLIT;
+            if (k_c >= chunks) { k_c = kk; ++fi_c; }
+            if (nviews > 0 && it + 1 < n_items) {
+                lbase = item_base(fi_c, k_c);
+                prime(lbase);
+            }
 
             // ---- epilogue: mean division (IEEE quotient) and one 16-byte store per cell ---------------------------
             if (p.mode == 1) {
@@ -372,10 +387,8 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                         }
                 }
             }
-            TOut* oc = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_c) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
-                       (k_c * 32 + lane) * VE;
-            k_c += KSPLIT;
-            if (k_c >= chunks) { k_c = kk; ++fi_c; }
+            TOut* oc = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_this) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
+                       (k_this * 32 + lane) * VE;
             if (j0 + CELLS <= p.Wb) {
 #pragma unroll
                 for (int c = 0; c < CELLS; ++c) {
