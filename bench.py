@@ -347,10 +347,12 @@ def run_ours(args, wl):
         dt = float(t.item())
         # the result really came back: compare one frame of the host output with the device-path output
         ok = bool(torch.equal(ho[B - 1], out[B - 1].permute(1, 2, 0).cpu()))
-        e2e = {"value": world * B * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": hf.numel() * hf.element_size(),
+        h2d = int(_lib.load().bevipm_host_last_h2d_bytes())   # what the entry really copied (sampled source-row spans only)
+        e2e = {"value": world * B * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "host_feature_bytes_per_step": hf.numel() * hf.element_size(),
                "d2h_bytes_per_step": ho.numel() * ho.element_size(), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
-               "api": "bevipm_warp_fuse_host (pinned host in -> H2D -> fused kernel -> D2H -> pinned host out, "
-                      "double-buffered per frame)", "matches_device_path": ok}
+               "api": "bevipm_warp_fuse_host (pinned host in -> H2D of the source-row spans any BEV cell samples -> fused kernel -> "
+                      "D2H -> pinned host out, double-buffered per frame)", "matches_device_path": ok}
         _lib.load().bevipm_host_release()
         barrier()
     clocks = sampler.stop() if sampler else None

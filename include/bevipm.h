@@ -137,6 +137,10 @@ int bevipm_deform_attn_fwd(const bevipm_deform_desc *d, const void *value, const
 int bevipm_warp_fuse_host(const bevipm_desc *d, const void *feats, const float *K, const float *Rt34,
                           const float *xs, const float *ys, void *out);
 void bevipm_host_release(void);
+/* Host-to-device bytes the last bevipm_warp_fuse_host call of this thread copied: the entry uploads, per frame,
+ * view and band of 16 source rows, only the span of texels some BEV cell samples (found by one small kernel from
+ * the calibration). */
+int64_t bevipm_host_last_h2d_bytes(void);
 
 #ifdef __cplusplus
 }

@@ -447,6 +447,38 @@ def test_host_buffer_entry_matches_oracle():
     assert _same(out.numpy().transpose(0, 3, 1, 2), want)
 
 
+def test_host_buffer_entry_uploads_only_sampled_texels():
+    """The host entry copies, per frame, view and band of source rows, only the span of texels some BEV cell samples.
+    Every texel NO cell samples is poisoned with NaN in the HOST buffer: the result must still be the oracle's on the
+    clean features, and the bytes copied must lie between the sampled texels and the sampled rows."""
+    from bevipm import _lib, ops
+    B, V, C, fhw, bhw = 2, 5, 32, (40, 64), (24, 72)
+    feats, K, Rt, xs, ys, img = _rig_case(B, V, C, fhw, bhw, seed=17)
+    want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")
+    ix, iy = orc.coords(K[:1], Rt[:1], xs, ys, fhw, img)
+    ix, iy = ix.reshape(V, *bhw), iy.reshape(V, *bhw)
+    nhwc = np.ascontiguousarray(feats.transpose(0, 1, 3, 4, 2))
+    touched, row_texels = 0, 0
+    for v in range(V):
+        x0, y0 = np.floor(ix[v]).astype(np.int64), np.floor(iy[v]).astype(np.int64)
+        hit = np.zeros(fhw, dtype=bool)
+        for dy in (0, 1):
+            for dx in (0, 1):
+                ok = (x0 + dx >= 0) & (x0 + dx < fhw[1]) & (y0 + dy >= 0) & (y0 + dy < fhw[0])
+                hit[(y0 + dy)[ok], (x0 + dx)[ok]] = True
+        nhwc[:, v][:, ~hit] = np.nan
+        touched += int(hit.sum())
+        row_texels += int(hit.any(axis=1).sum()) * fhw[1]
+    assert touched < row_texels < V * fhw[0] * fhw[1]
+    host = torch.from_numpy(nhwc).pin_memory()
+    out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                             torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+    assert _same(out.numpy().transpose(0, 3, 1, 2), want)
+    calib_bytes = (B * V * 21 + bhw[0] + bhw[1]) * 4
+    copied = int(_lib.load().bevipm_host_last_h2d_bytes()) - calib_bytes
+    assert B * touched * C * 4 <= copied <= B * row_texels * C * 4
+
+
 def test_library_was_the_thing_that_ran():
     from bevipm import _lib
     before = _lib.launch_count()

@@ -28,7 +28,7 @@ class Desc(ctypes.Structure):
 EXPORTS = (
     "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
-    "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant",
+    "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant", "bevipm_host_last_h2d_bytes",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -53,6 +53,7 @@ def load() -> ctypes.CDLL:
     L.bevipm_last_error.restype = ctypes.c_char_p
     L.bevipm_launch_count.restype = ctypes.c_int64
     L.bevipm_last_variant.restype = ctypes.c_int32
+    L.bevipm_host_last_h2d_bytes.restype = ctypes.c_int64
     L.bevipm_warp_fuse_fwd.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp]
     L.bevipm_warp_fuse_bwd.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp]
     L.bevipm_sample_coords.argtypes = [dp, fp, fp, fp, fp, fp, fp, vp]

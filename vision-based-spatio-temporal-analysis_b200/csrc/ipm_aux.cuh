@@ -161,6 +161,33 @@ __global__ void sample_coords_kernel(const FwdParams p, float* __restrict__ ix, 
     iy[(long long)bv * p.Hb * p.Wb + cell] = y;
 }
 
+// Source texels any BEV cell samples, per (frame, view) and source row: span[(bv * Hf + y) * 2] = first,
+// [.. + 1] = last x holding an in-map tap (first > last: nothing on that row).  Same projection and tap validity
+// as the fused kernels; the host-buffer entry uploads only these spans (rows above the horizon of a ground-plane
+// homography are never read).  span[] must be preset to {INT_MAX, -1}.
+__global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span) {
+    const int bv = blockIdx.y;
+    __shared__ float H[9];
+    if (threadIdx.x == 0) homography(p.K + 9 * bv, p.Rt + 12 * bv, H);
+    __syncthreads();
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= p.Hb * p.Wb) return;
+    const int i = cell / p.Wb, j = cell - i * p.Wb;
+    float x, y;
+    cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y);
+    const CellTap t = make_tap(x, y, p.Wf, p.Hf);
+    const int tm = t.flags & kTapMask;
+    if (!tm) return;
+    int* sv = span + (long long)bv * p.Hf * 2;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+        if (!((tm >> tap) & 1)) continue;
+        const int yy = t.y0 + (tap >> 1), xx = t.x0 + (tap & 1);
+        atomicMin(sv + 2 * yy, xx);
+        atomicMax(sv + 2 * yy + 1, xx);
+    }
+}
+
 // fusion.py:17-22 on materialised maps: in [B,V,inner] -> out [B,inner]; sequential over v.
 template <typename TIn, typename TOut>
 __global__ void __launch_bounds__(256) fuse_views_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int V,
