@@ -543,7 +543,8 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
         FwdParams pr = make_params(&d, nullptr, dK, dRt, dxs, dys, nullptr);
         dim3 grid(ceil_div(d.Hb * d.Wb, 256), (unsigned)(d.B * d.V));
         if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B*V too large");
-        bevipm::touched_spans_kernel<<<grid, 256, 0, A.st[0]>>>(pr, A.rows);
+        if ((size_t)d.Hf * 8 > 40 * 1024) return fail(BEVIPM_ERR_UNSUPPORTED, "Hf=%d too tall for the span table of the host entry", d.Hf);
+        bevipm::touched_spans_kernel<<<grid, 256, (size_t)d.Hf * 2 * sizeof(int), A.st[0]>>>(pr, A.rows);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(A.rows_host, A.rows, nbv * 2 * sizeof(int), cudaMemcpyDeviceToHost, A.st[0]));

@@ -166,25 +166,34 @@ __global__ void sample_coords_kernel(const FwdParams p, float* __restrict__ ix, 
 // as the fused kernels; the host-buffer entry uploads only these spans (rows above the horizon of a ground-plane
 // homography are never read).  span[] must be preset to {INT_MAX, -1}.
 __global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span) {
+    extern __shared__ int s_span[];  // [Hf][2]: this block's spans, flushed once (few rows per block are touched)
     const int bv = blockIdx.y;
     __shared__ float H[9];
     if (threadIdx.x == 0) homography(p.K + 9 * bv, p.Rt + 12 * bv, H);
+    for (int y = threadIdx.x; y < p.Hf; y += blockDim.x) { s_span[2 * y] = 0x7fffffff; s_span[2 * y + 1] = -1; }
     __syncthreads();
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cell >= p.Hb * p.Wb) return;
-    const int i = cell / p.Wb, j = cell - i * p.Wb;
-    float x, y;
-    cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y);
-    const CellTap t = make_tap(x, y, p.Wf, p.Hf);
-    const int tm = t.flags & kTapMask;
-    if (!tm) return;
-    int* sv = span + (long long)bv * p.Hf * 2;
+    if (cell < p.Hb * p.Wb) {
+        const int i = cell / p.Wb, j = cell - i * p.Wb;
+        float x, y;
+        cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y);
+        const CellTap t = make_tap(x, y, p.Wf, p.Hf);
+        const int tm = t.flags & kTapMask;
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
-        if (!((tm >> tap) & 1)) continue;
-        const int yy = t.y0 + (tap >> 1), xx = t.x0 + (tap & 1);
-        atomicMin(sv + 2 * yy, xx);
-        atomicMax(sv + 2 * yy + 1, xx);
+        for (int tap = 0; tap < 4; ++tap) {
+            if (!((tm >> tap) & 1)) continue;
+            const int yy = t.y0 + (tap >> 1), xx = t.x0 + (tap & 1);
+            atomicMin(s_span + 2 * yy, xx);
+            atomicMax(s_span + 2 * yy + 1, xx);
+        }
+    }
+    __syncthreads();
+    int* sv = span + (long long)bv * p.Hf * 2;
+    for (int y = threadIdx.x; y < p.Hf; y += blockDim.x) {
+        if (s_span[2 * y] <= s_span[2 * y + 1]) {
+            atomicMin(sv + 2 * y, s_span[2 * y]);
+            atomicMax(sv + 2 * y + 1, s_span[2 * y + 1]);
+        }
     }
 }
 
