@@ -242,6 +242,8 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 25: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 8, 2>(p, st);
         case 26: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 8, 1>(p, st);
         case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
+        // run kernel <cells per segment, warps per CTA, warps per segment, register cap, ring depth, .ca>:
+        // 32 = fp32 default, 33 = bf16 default; the others are the sweep points quoted in profiles/r01_notes.md
         case 30: return launch_run<TIn, TOut, 8, 4, 4, 128, 5, false>(p, st);
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
         case 32: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);

@@ -8,18 +8,20 @@
 // 2.4x (config 2) on average (tools/reuse_stats.py), so this kernel walks VIEW-major and keeps the
 // unpacked block in registers for as long as the row stays inside it:
 //
-//   phase A (whole CTA): thread = (row segment, view, cell); project once, mark the cell-views some
-//            view sees and, among them, the ones that START a new 2x2 block ("reloads": the cell
-//            before is not seen or sits in another block).  Two tables per row segment go to shared
-//            memory: per-(view, cell) blend weights, and the compact LOAD LIST (tap offsets of every
-//            reload, in walking order: views ascending, cells ascending).
-//   phase B (per warp = row segment x 512-byte channel chunk): accumulators of all CELLS cells live
-//            in registers; for each view that sees the segment, for each cell (unrolled, so the
-//            accumulator index is static): on a reload bit, unpack the block that is in flight into
-//            the `cur` registers and request the NEXT entry of the load list into the raw registers
-//            just freed (one batch outstanding, flying during the blends up to the next reload);
-//            then blend `cur` with the cell's weights and add to the cell's accumulator.  Per cell
-//            the views are still added in ascending order: the reference's accumulation order.
+//   phase A (the first warp of every row segment; no block barrier when one warp owns a segment):
+//            lane = (view, cell); project once (homographies come from a table built once per CTA), mark
+//            the cell-views some view sees and, among them, the ones that START a new 2x2 block
+//            ("reloads": the cell before is not seen or sits in another block).  Ballot prefix sums put
+//            three tables of the segment into shared memory, directly in walking order (views ascending,
+//            cells ascending): per-(view, cell) blend weights, the LOAD LIST (tap offsets of every reload)
+//            and the list of views that see the segment with their seen / reload bit masks.
+//   phase B (per warp = row segment x 512-byte channel chunk, chunks one after the other): accumulators
+//            of all CELLS cells live in registers; for each view of the view list, for each cell
+//            (unrolled, so the accumulator index is static): on a reload bit, read the oldest block of
+//            the warp's cp.async ring, unpack it once into the `cur` registers and hand the load-list
+//            entry DEPTH-1 ahead to the copy engine; then blend `cur` with the cell's weights and add
+//            to the cell's accumulator (predicated on "seen").  Per cell the views are still added in
+//            ascending order: the reference's accumulation order.
 //   A tap outside the map gets weight 0 and the address of one of the block's in-map taps (exactly +0
 //   for finite features, as in the list kernel).
 #pragma once
@@ -40,7 +42,7 @@ __host__ __device__ constexpr int run_seg_bytes(int V, int cells) {
            + ((V * 8 + 8 + 15) / 16) * 16;   // per-view masks, compact view list, two totals
 }
 
-// ---- async-copy ring helpers (DEPTH > 0) ------------------------------------------------------------
+// ---- async-copy ring helpers ------------------------------------------------------------------------
 template <bool CA>
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
     if constexpr (CA) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
