@@ -458,6 +458,8 @@ int bevipm_deform_attn_fwd(const bevipm_deform_desc* d, const void* value, const
     p.value = value; p.shapes = shapes; p.start = reinterpret_cast<const long long*>(level_start); p.loc = loc; p.attn = attn; p.out = out;
     p.B = d->B; p.Q = d->Q; p.M = d->M; p.D = d->D; p.L = d->L; p.P = d->P; p.S = d->S;
     const int lph = d->D * esz / 16;
+    // tap positions are 32-bit counts of 16-byte vectors inside one frame
+    if ((long long)d->S * d->M * lph > 0x7fffffffLL) return fail(BEVIPM_ERR_UNSUPPORTED, "value maps too large for 32-bit tap offsets");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool v32 = d->value_dtype == BEVIPM_F32, o32 = d->out_dtype == BEVIPM_F32;
     if (v32 && o32) return launch_deform<float, float>(p, lph, st);
