@@ -229,6 +229,20 @@ def test_default_dispatch_random_shapes(seed):
     assert _same(out, want), (B, V, C, fhw, bhw, mode, bf16)
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("variant", [0, 21, 1])
+def test_max_fusion_all_three_kernels(dtype, variant):
+    """fusion.py:22 on a run-kernel-eligible shape: variant 0 = run kernel, 21 = list kernel, 1 = tile kernel.
+    The rig has views that miss cells (their zero padding takes part in the maximum) and cells no view sees."""
+    feats, K, Rt, xs, ys, img = _rig_case(2, 7, 256, (31, 53), (37, 91), seed=23)
+    feats = feats - 1.5   # mostly negative values: the zeros of missing views must win there
+    f = torch.from_numpy(feats).to(dtype).float().numpy()
+    want = orc.warp_fuse(f, K, Rt, xs, ys, img, "max")
+    assert (want == 0).any() and (want < 0).any() and (want > 0).any()
+    out = _run(f, K, Rt, xs, ys, img, "max", True, dtype=dtype, variant=variant).cpu().numpy()
+    assert _same(out, want)
+
+
 @pytest.mark.parametrize("views", [1, 2, 9, 16])
 def test_run_kernel_view_counts(views):
     feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)

@@ -153,25 +153,25 @@ int launch_list(FwdParams p, cudaStream_t st) {
 template <typename TIn>
 bool run_kernel_ok(const FwdParams& p) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
-    if (p.mode != BEVIPM_SUM && p.mode != BEVIPM_MEAN) return false;
+    if (p.mode != BEVIPM_SUM && p.mode != BEVIPM_MEAN && p.mode != BEVIPM_MAX) return false;
     if (p.V > bevipm::kRunMaxViews) return false;
     if (p.C % (32 * VE)) return false;  // whole 512-byte channel chunks only
     return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
 }
 
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0>
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = bevipm::KM_ACC>
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
-    if (!run_kernel_ok<TIn>(p))
-        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs sum/mean, V <= %d, C a multiple of %d, 32-bit tap offsets",
+    if (!run_kernel_ok<TIn>(p) || (p.mode == BEVIPM_MAX) != (KMODE == bevipm::KM_MAX))
+        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs sum/mean/max, V <= %d, C a multiple of %d, 32-bit tap offsets",
                     bevipm::kRunMaxViews, 32 * VE);
     p.tiles_x = ceil_div(p.Wb, CELLS);
     p.tiles_y = ceil_div(p.Hb, R);
     p.fsy16 = (int)(p.fs_y / VE);
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
-    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE>;
+    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE>;
     const size_t smem = (size_t)R * bevipm::run_seg_bytes(p.V, CELLS) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48;  // tables, rings, homographies
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
@@ -199,6 +199,13 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
                                (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
         if (variant == 1 || span > 0x7fffffffLL) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st); }
+        // measured (tools/bench_modes.py, run vs list): c1 0.102 / 0.091 ms, c2 0.785 / 0.786, c3 0.278 / 0.356 -> the run
+        // kernel's max walk except for fp32 texels of 2 KB and more
+        if (variant != 21 && run_kernel_ok<TIn>(p) && !(sizeof(TIn) == 4 && (long long)p.C * 4 >= 2048)) {
+            if (sizeof(TIn) == 4) { g_last_variant = 32; return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_MAX>(p, st); }
+            g_last_variant = 33;
+            return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, bevipm::KM_MAX>(p, st);
+        }
         const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
         if (texel_bytes >= 2048) { g_last_variant = 21; return launch_list<TIn, TOut, 4, bevipm::KM_MAX, 4, 3>(p, st); }
         if (texel_bytes >= 1024) { g_last_variant = 23; return launch_list<TIn, TOut, 2, bevipm::KM_MAX, 4, 4>(p, st); }

@@ -73,6 +73,13 @@ template <> struct VecTraits<__nv_bfloat16> {
 
 __device__ __forceinline__ uint4 ldg16(const uint4* p) { return __ldg(p); }
 
+// torch.max semantics in one instruction: NaN if either operand is NaN (fusion.py:22 propagates NaN)
+__device__ __forceinline__ float max_nan(float a, float b) {
+    float d;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
 // P float2 pairs -> global memory as TOut, streaming (written once, never re-read by us)
 template <typename TOut, int P>
 __device__ __forceinline__ void store_pairs(TOut* dst, const float2 (&f)[P]) {

@@ -87,8 +87,8 @@ __device__ __forceinline__ void walk_steps(const FwdParams& p, const StepRec* st
             for (int e = 0; e < P; ++e) {
                 if constexpr (KMODE == KM_MAX) {
                     float2& mx = acc[nn][e];
-                    mx.x = (o[nn][e].x > mx.x || o[nn][e].x != o[nn][e].x) ? o[nn][e].x : mx.x;
-                    mx.y = (o[nn][e].y > mx.y || o[nn][e].y != o[nn][e].y) ? o[nn][e].y : mx.y;
+                    mx.x = max_nan(mx.x, o[nn][e].x);
+                    mx.y = max_nan(mx.y, o[nn][e].y);
                 } else {
                     acc[nn][e] = __fadd2_rn(acc[nn][e], o[nn][e]);  // fusion.py:18-21, view order kept
                 }
@@ -101,8 +101,8 @@ __device__ __forceinline__ void walk_steps(const FwdParams& p, const StepRec* st
                     if (m & 0x200) {  // fusion.py:22: the zeros of views that miss the cell take part
 #pragma unroll
                         for (int e = 0; e < P; ++e) {
-                            acc[nn][e].x = (0.0f > acc[nn][e].x) ? 0.0f : acc[nn][e].x;
-                            acc[nn][e].y = (0.0f > acc[nn][e].y) ? 0.0f : acc[nn][e].y;
+                            acc[nn][e].x = max_nan(acc[nn][e].x, 0.0f);
+                            acc[nn][e].y = max_nan(acc[nn][e].y, 0.0f);
                         }
                     }
                 } else if (p.mode == 1) {

@@ -39,7 +39,7 @@ constexpr int kRunMaxViews = 16;
 __host__ __device__ constexpr int run_seg_bytes(int V, int cells) {
     return V * cells * 16                    // blend weights (nw, ne, sw, se) of every (view, cell)
            + (V * cells + 8) * 16            // the load list (+8: entries the walk reads ahead but never copies)
-           + ((V * 8 + 8 + 15) / 16) * 16;   // per-view masks, compact view list, two totals
+           + ((V * 8 + 12 + 15) / 16) * 16;  // per-view masks, compact view list, two totals, cells every view sees
 }
 
 // ---- async-copy ring helpers ------------------------------------------------------------------------
@@ -94,7 +94,8 @@ __device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long bas
 // the normal case (wildtrack_loader.py:291-293 reads one calibration per camera).
 // PROBE (timing aid, results are NOT the fusion): 1 = no copies are issued (instruction side alone), 2 = copies and
 // unpack but no blend (memory side alone)
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0>
+// KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views, zeros of views that miss a cell included (fusion.py:22).
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC>
 __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
     static_assert(DEPTH >= 2 && DEPTH <= 8, "ring depth");
     using VT = VecTraits<TIn>;
@@ -120,7 +121,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     auto seg_loads = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 16); };
     auto seg_meta = [&](int r) { return reinterpret_cast<int*>(smem_raw + r * seg_bytes + V * CELLS * 16 + (V * CELLS + 8) * 16); };
     // meta: [0, V) per-view mask (seen | reload << 16), [V, 2V) the views that see the segment, [2V] their
-    // number, [2V+1] entries of the load list
+    // number, [2V+1] entries of the load list, [2V+2] mask of the cells EVERY view sees (max fusion)
 
     const int fsv16 = (int)(p.fs_v / VE);
     const int r = warp / KSPLIT, kk = warp - r * KSPLIT;
@@ -158,6 +159,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
             const int gl = lane / CELLS, c = lane - gl * CELLS;
             const unsigned lt = (1u << lane) - 1u;
             int nloads = 0, nseen = 0;  // warp-uniform running totals
+            unsigned all_seen = CMASK;  // cells every view sees
             for (int v0 = 0; v0 < V; v0 += GPW) {
                 const int v = v0 + gl;
                 const bool active = gl < GPW && v < V;
@@ -207,8 +209,13 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 }
                 nloads += __popc(reload_b);
                 nseen += __popc(lead_b);
+                if (KMODE == KM_MAX) {
+#pragma unroll
+                    for (int gq = 0; gq < GPW; ++gq)
+                        if (v0 + gq < V) all_seen &= (seen_b >> (gq * CELLS)) & CMASK;
+                }
             }
-            if (lane == 0) { ml[2 * V] = nseen; ml[2 * V + 1] = nloads; }
+            if (lane == 0) { ml[2 * V] = nseen; ml[2 * V + 1] = nloads; ml[2 * V + 2] = (int)all_seen; }
             if (lane < 8) loads[nloads + lane] = make_int4(-1, 0, 0, 0);  // end of list
         }
         if (KSPLIT > 1) __syncthreads();
@@ -269,7 +276,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
 #pragma unroll
             for (int c = 0; c < CELLS; ++c)
 #pragma unroll
-                for (int q = 0; q < P; ++q) acc[c][q] = make_float2(0.0f, 0.0f);
+                for (int q = 0; q < P; ++q) acc[c][q] = (KMODE == KM_MAX) ? make_float2(-INFINITY, -INFINITY) : make_float2(0.0f, 0.0f);
 
             if (nviews > 0) {
                 float2 cur[4][P];
@@ -335,7 +342,15 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                                 for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
 #pragma unroll
                                 for (int q = 0; q < ILP; ++q)
-                                    if (seen) acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
+                                    if (seen) {
+                                        if constexpr (KMODE == KM_MAX) {  // fusion.py:22, NaN propagates like torch.max
+                                            float2& mx = acc[c][q0 + q];
+                                            mx.x = max_nan(mx.x, sv[q].x);
+                                            mx.y = max_nan(mx.y, sv[q].y);
+                                        } else {
+                                            acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
+                                        }
+                                    }
                             }
                         }
                     }
@@ -352,7 +367,19 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
             }
 
             // ---- epilogue: mean division (IEEE quotient) and one 16-byte store per cell ---------------------------
-            if (p.mode == 1) {
+            if constexpr (KMODE == KM_MAX) {
+                // a view that misses the cell contributes its zero padding to the maximum (geometry.py:94 + fusion.py:22)
+                const unsigned every = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_meta + 8 * V + 8), 0);
+#pragma unroll
+                for (int c = 0; c < CELLS; ++c)
+                    if (!((every >> c) & 1u)) {
+#pragma unroll
+                        for (int q = 0; q < P; ++q) {
+                            acc[c][q].x = max_nan(acc[c][q].x, 0.0f);
+                            acc[c][q].y = max_nan(acc[c][q].y, 0.0f);
+                        }
+                    }
+            } else if (p.mode == 1) {
                 // Markstein's 3-op division is exact for finite sums (ipm_fused.cuh div_exact_vec); +-Inf would
                 // turn into NaN.  One test per chunk: the packed sum of all CELLS x 8 accumulators is finite
                 // only if every one of them is (Inf - Inf = NaN; a finite overflow merely takes the slow path).
