@@ -172,7 +172,7 @@ int launch_run(FwdParams p, cudaStream_t st) {
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
     auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE>;
-    const size_t smem = (size_t)R * bevipm::run_seg_bytes(p.V, CELLS) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48;  // tables, rings, homographies
+    const size_t smem = (size_t)bevipm::run_tables_bytes(p.V, CELLS, R) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48;  // tables, rings, homographies
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
     // at least ~16 CTA waves so the tail stays small
