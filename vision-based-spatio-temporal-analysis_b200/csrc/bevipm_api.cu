@@ -159,7 +159,7 @@ bool run_kernel_ok(const FwdParams& p) {
     return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
 }
 
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = bevipm::KM_ACC>
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = bevipm::KM_ACC, bool TMA = false>
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
@@ -171,8 +171,8 @@ int launch_run(FwdParams p, cudaStream_t st) {
     p.fsy16 = (int)(p.fs_y / VE);
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
-    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE>;
-    const size_t smem = (size_t)bevipm::run_tables_bytes(p.V, CELLS, R) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48;  // tables, rings, homographies
+    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE, TMA>;
+    const size_t smem = (size_t)bevipm::run_tables_bytes(p.V, CELLS, R) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8;  // tables, rings, homographies, ring barriers
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
     // at least ~16 CTA waves so the tail stays small
@@ -257,10 +257,10 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
         case 34: return launch_run<TIn, TOut, 8, 4, 1, 128, 5, false>(p, st);
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
-        case 36: return launch_run<TIn, TOut, 8, 4, 1, 96, 3, false>(p, st);
+        case 36: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_ACC, true>(p, st);    // TMA ring
         case 37: return launch_run<TIn, TOut, 16, 4, 1, 128, 4, false>(p, st);
         case 38: return launch_run<TIn, TOut, 16, 4, 1, 168, 4, false>(p, st);
-        case 39: return launch_run<TIn, TOut, 8, 4, 1, 128, 6, false>(p, st);
+        case 39: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, bevipm::KM_ACC, true>(p, st);   // TMA ring
         case 40: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 1>(p, st);  // timing probes (not the fusion)
         case 41: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false, 2>(p, st);
         case 11: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_PROBE, 4, false>(p, st);  // loads-only timing probes

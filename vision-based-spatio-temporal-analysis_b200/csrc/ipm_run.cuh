@@ -92,6 +92,26 @@ __device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long bas
     cp_async16<CA>(stage + 1536, tap_ptr(base, o.w));
 }
 
+// ---- TMA form of the ring (template flag TMA): one elected lane hands the copy engine four 512-byte bulk copies per
+// load-list entry (cp.async.bulk global -> shared, completion counted on the stage's mbarrier in bytes); the warp
+// waits on the barrier's phase parity instead of a cp.async group.  No LSU / L1 tag work for the loads at all.
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy512(uint32_t dst, const void* src, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], 512, [%2];" ::"r"(dst), "l"(src), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+        if (spin > (1 << 24)) __trap();  // a lost copy must not hang the device
+    }
+}
+
 // A per-warp ring of DEPTH 2-KB stages in shared memory is filled by cp.async (.ca when CA, else .cg), DEPTH-1
 // blocks in flight per warp; every lane reads back exactly the 16 bytes it copied, so no barrier is involved.
 // One CTA walks `fpc` consecutive frames of its tile and re-uses the phase A tables for as long as the
@@ -100,9 +120,10 @@ __device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long bas
 // PROBE (timing aid, results are NOT the fusion): 1 = no copies are issued (instruction side alone), 2 = copies and
 // unpack but no blend (memory side alone)
 // KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views, zeros of views that miss a cell included (fusion.py:22).
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC>
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC, bool TMA = false>
 __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
     static_assert(DEPTH >= 2 && DEPTH <= 8, "ring depth");
+    static_assert(!TMA || (DEPTH & (DEPTH - 1)) == 0, "the TMA ring indexes its stages with a mask");
     using VT = VecTraits<TIn>;
     constexpr int VE = VT::VE, P = VT::P;
     constexpr int R = NW / KSPLIT;  // row segments per CTA
@@ -139,6 +160,18 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     // DEPTH > 0: this lane's 16 bytes of stage 0 / tap 0 in the warp's ring (stage = 2 KB, tap = 512 B)
     uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + run_tables_bytes(V, CELLS, R) + warp * (DEPTH * 2048) + lane * 16;
     asm volatile("" : "+r"(ring));  // opaque: one register, not re-derived from %tid at every reload
+    // TMA: one mbarrier per stage of this warp's ring, behind the homography table; entries issued / consumed so far
+    uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_raw) + run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048) + V * 48 + warp * (DEPTH * 8);
+    uint32_t n_issue = 0, n_cons = 0;
+    if constexpr (TMA) {
+        if (lane == 0) {
+#pragma unroll
+            for (int s = 0; s < DEPTH; ++s) mbar_init(bars + s * 8, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        asm volatile("" : "+r"(bars));
+    }
 
     const int cpw = (chunks - kk + KSPLIT - 1) / KSPLIT;  // 512-byte chunks this warp walks per frame
 
@@ -266,12 +299,31 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
         // entries 0 .. DEPTH-2 of the load list start flying: one commit group per entry (past the end of the list
         // the entries carry x = -1: nothing is copied, the group is empty).  Called before the first item and, for
         // every later item, right after the walk of the one before it: the copies fly during that item's epilogue.
+        // TMA: lane 0 arms the stage's barrier with the entry's 2048 bytes and issues the four bulk copies (its own `ring`
+        // and lane base are the warp's: lane offset 0); the stage was read by every lane at an earlier reload
+        auto issue_tma = [&](unsigned long long base, const int4& o) {
+            __syncwarp();
+            if (lane == 0) {
+                const uint32_t st = n_issue & (DEPTH - 1), bar = bars + st * 8, dst = ring + st * 2048;
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(bar, 2048);
+                bulk_copy512(dst, tap_ptr(base, o.x), bar);
+                bulk_copy512(dst + 512, tap_ptr(base, o.y), bar);
+                bulk_copy512(dst + 1024, tap_ptr(base, o.z), bar);
+                bulk_copy512(dst + 1536, tap_ptr(base, o.w), bar);
+            }
+            ++n_issue;
+        };
         auto prime = [&](unsigned long long base) {
 #pragma unroll
             for (int s = 0; s < DEPTH - 1; ++s) {
                 const int4 o = lds16i(s_loads + s * 16);
-                if (PROBE != 1 && o.x >= 0) run_copy4<CA>(ring + s * 2048, base, o);
-                cp_async_commit();
+                if constexpr (TMA) {
+                    if (PROBE != 1 && o.x >= 0) issue_tma(base, o);
+                } else {
+                    if (PROBE != 1 && o.x >= 0) run_copy4<CA>(ring + s * 2048, base, o);
+                    cp_async_commit();
+                }
             }
         };
         unsigned long long lbase = item_base(0, kk);
@@ -308,6 +360,21 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                         const bool rl_now = rl;
                         if (c + 1 < CELLS) rl = (m >> (17 + c)) & 1u;          // decided one cell early
                         if (rl_now) {                                          // the row leaves the block held in `cur`
+                            if constexpr (TMA) {
+                                const uint32_t stc = n_cons & (DEPTH - 1);
+                                mbar_wait(bars + stc * 8, (n_cons / DEPTH) & 1u);  // the entry's 2048 bytes have landed
+                                const uint32_t sr = ring + stc * 2048;
+                                uint4 nxt[4];
+                                nxt[0] = lds16(sr); nxt[1] = lds16(sr + 512);
+                                nxt[2] = lds16(sr + 1024); nxt[3] = lds16(sr + 1536);
+                                const int4 o = lds16i(lp);
+#pragma unroll
+                                for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
+                                ++n_cons;
+                                // the entry DEPTH-1 ahead goes into the stage unpacked at the previous reload
+                                if (PROBE != 1 && o.x >= 0) issue_tma(lbase, o);
+                                lp += 16;
+                            } else {
                             cp_async_wait<DEPTH - 2>();  // the oldest entry has landed (a lane reads back its own bytes)
                             uint4 nxt[4];
                             nxt[0] = lds16(st_rd); nxt[1] = lds16(st_rd + 512);
@@ -321,6 +388,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                             lp += 16;
                             st_wr = st_rd;
                             st_rd = (st_rd == ring + (DEPTH - 1) * 2048) ? ring : st_rd + 2048;
+                            }
                         }
                         if constexpr (PROBE == 2) {
                             if (rl_now) {
@@ -360,7 +428,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                         }
                     }
                 }
-                cp_async_wait<0>();  // (only empty groups are left) the ring restarts with the next item
+                if constexpr (!TMA) cp_async_wait<0>();  // (only empty groups are left) the ring restarts with the next item
             }
             // the item after this one: its first blocks fly while this item is divided, packed and stored
             const int k_this = k_c, fi_this = fi_c;
