@@ -74,32 +74,9 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
 // ---- fused NHWC fast path ---------------------------------------------------------------------
-// variant ids (bevipm_desc.variant); 0 = auto.  {vectors per lane, cells per warp walk, min CTAs/SM}
-struct Variant { int nv, cells, minb, pipe; };
-constexpr Variant kVariants[] = {
-    {0, 0, 0, 0},  // 0: auto
-    {1, 2, 4, 0},  // 1
-    {1, 2, 3, 1},  // 2
-    {2, 4, 2, 0},  // 3
-    {1, 4, 3, 0},  // 4
-    {2, 2, 2, 0},  // 5
-    {2, 2, 2, 1},  // 6
-    {4, 1, 2, 0},  // 7
-    {2, 1, 3, 0},  // 8
-    {4, 2, 1, 0},  // 9
-    {1, 4, 2, 1},  // 10
-    {1, 2, 4, 0},  // 11..14: loads-only timing probes (results are NOT the fusion)
-    {2, 2, 2, 0},
-    {2, 2, 2, 1},
-    {4, 2, 2, 0},
-    {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0},  // 15..19 unused
-    {4, 4, 2, 1}, {4, 4, 3, 1}, {2, 4, 3, 1}, {2, 4, 4, 1}, {1, 4, 6, 1}, {2, 8, 2, 1}, {4, 8, 1, 1}, {1, 4, 4, 1},  // 20..27: list kernel {NV, warps, minb}
-    {0, 0, 0, 0}, {0, 0, 0, 0},                                                                                      // 28, 29 unused
-    {8, 4, 3, 2}, {8, 4, 4, 2}, {8, 2, 3, 2}, {8, 1, 3, 2}, {8, 1, 4, 2}, {16, 1, 3, 2}, {16, 2, 3, 2}, {16, 4, 2, 2},  // 30..37: run kernel {cells, ksplit, minb} (+ ring depth, .ca/.cg: see dispatch_fused)
-    {8, 2, 4, 2}, {16, 4, 3, 2},                                                                                        // 38, 39
-    {8, 4, 4, 3}, {8, 4, 4, 3},                                                                                         // 40, 41: run-kernel timing probes
-};
-constexpr int kNumVariants = sizeof(kVariants) / sizeof(kVariants[0]);
+// variant ids (bevipm_desc.variant); 0 = auto.  1..10 tile kernel shapes, 11..14 its loads-only timing probes,
+// 20..27 list kernel shapes, 30..39 run kernel shapes, 40 / 41 its timing probes: see dispatch_fused.
+constexpr int kNumVariants = 42;
 constexpr int kTH = 8;
 
 template <typename TIn, typename TOut, int NV, int CELLS, int KMODE, int MINB, bool PIPE>
