@@ -93,6 +93,28 @@ def test_golden_backward(golden, case, mode, channels_last):
     assert np.abs(got - ref).max() <= 1e-5 * np.abs(ref).max()   # atomics: order differs, tolerance 1e-5 rel
 
 
+@pytest.mark.parametrize("mode", ["sum", "mean", "none"])
+@pytest.mark.parametrize("generic", [False, True])
+def test_backward_run_kernel_and_generic_kernel_vs_oracle(monkeypatch, mode, generic):
+    """Gradient w.r.t. the features on a shape the run-kernel backward takes (channels-last, C = 256): both the
+    run-kernel backward (block-wise pre-reduction, then atomics) and the generic one must match the oracle's
+    autograd restatement within 1e-5 relative (sums are re-associated by the atomics anyway)."""
+    from bevipm import _lib, ops
+    monkeypatch.setenv("BEVIPM_BWD_GENERIC", "1" if generic else "0")
+    feats, K, Rt, xs, ys, img = _rig_case(2, 7, 256, (31, 53), (37, 91), seed=29)
+    f, Kd, Rd, xd, yd = _dev_inputs(feats, K, Rt, xs, ys, True)
+    f.requires_grad_(True)
+    out = ops.warp_fuse(f, Kd, Rd, xd, yd, int(img[0]), int(img[1]), _lib.MODES[mode], False, 0)
+    torch.manual_seed(3)
+    cot = torch.randn_like(out)   # same (channels-last) strides as the output: what the fast paths take
+    (out * cot).sum().backward()
+    got = f.grad.cpu().numpy()
+    want = orc.warp_fuse_bwd(np.ascontiguousarray(cot.cpu().numpy()), K, Rt, xs, ys, feats.shape, img, mode)
+    assert got.shape == want.shape
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
+    assert np.array_equal(got == 0, want == 0) or np.abs(got[(got == 0) != (want == 0)]).max() <= 1e-5 * np.abs(want).max()
+
+
 # ---- every fused-kernel variant against the oracle, ragged shapes --------------------------------
 
 @pytest.mark.parametrize("variant", list(range(1, 11)) + list(range(20, 28)))

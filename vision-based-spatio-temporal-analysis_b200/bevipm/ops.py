@@ -111,6 +111,12 @@ def warp_fuse_bwd(grad_out: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, x
     per_view = mode == _lib.NONE
     if grad_out.dtype not in _DT:
         grad_out = grad_out.float()
+    if channels_last and grad_out.stride(-3 if not per_view else 2) != 1:
+        # channels-last features want a channels-last dL/dBEV (the vectorised kernels); one transpose of the BEV-sized
+        # gradient is cheaper than the strided scatter
+        perm = (0, 1, 3, 4, 2) if per_view else (0, 2, 3, 1)
+        inv = (0, 1, 4, 2, 3) if per_view else (0, 3, 1, 2)
+        grad_out = grad_out.permute(*perm).contiguous().permute(*inv)
     with torch.cuda.device(grad_out.device):
         if channels_last:
             g = torch.zeros((B, V, Hf, Wf, C), device=grad_out.device, dtype=torch.float32).permute(0, 1, 4, 2, 3)

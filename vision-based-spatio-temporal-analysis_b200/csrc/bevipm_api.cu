@@ -12,6 +12,7 @@
 #include "ipm_fused.cuh"
 #include "ipm_list.cuh"
 #include "ipm_run.cuh"
+#include "ipm_run_bwd.cuh"
 #include "deform_attn.cuh"
 
 namespace {
@@ -354,9 +355,31 @@ int bevipm_warp_fuse_bwd(const bevipm_desc* d, const void* grad_out, const float
     bool vec = d->fs_c == 1 && d->os_c == 1 && d->C % 4 == 0 && aligned16(grad_feats);
     const int64_t fs[] = {d->fs_b, d->fs_v, d->fs_y, d->fs_x};
     for (int64_t s : fs) if (s % 4) vec = false;
+    // run-kernel backward (contributions of a row's cells summed per 2x2 block in registers before the atomics):
+    // channels-last fp32 gradient, whole 128-channel chunks, V <= 16; d->variant == 1 forces the generic kernel
+    const long long span16 = (long long)d->V * (d->fs_v / 4) + (long long)(d->Hf + 2) * (d->fs_y / 4) + (long long)(d->Wf + 2) * (d->fs_x / 4);
+    const int og = g32 ? 4 : 4;  // grad_out is read 4 channels at a time: 16 bytes (fp32) or 8 bytes (bf16)
+    const char* force_generic = getenv("BEVIPM_BWD_GENERIC");  // A/B aid (tools/bench_backward.py)
+    bool run_ok = vec && d->variant != 1 && !(force_generic && force_generic[0] == '1') && d->C % 128 == 0 && d->V <= bevipm::kRunMaxViews && span16 <= 0x7fffffffLL &&
+                  d->fs_y >= 0 && d->fs_x >= 0 && d->os_x % og == 0 && d->os_y % og == 0 && d->os_b % og == 0 && d->os_v % og == 0 &&
+                  (reinterpret_cast<uintptr_t>(grad_out) & (g32 ? 15 : 7)) == 0;
+    if (run_ok) {
+        constexpr int CELLS = 8, NW = 4;
+        p.tiles_x = ceil_div(p.Wb, CELLS);
+        p.tiles_y = ceil_div(p.Hb, NW);
+        p.fsy16 = (int)(p.fs_y / 4);
+        p.fsx16 = (int)(p.fs_x / 4);
+        p.rcpV = 1.0f / (float)p.V;
+        const size_t rsmem = (size_t)bevipm::run_tables_bytes(p.V, CELLS, NW) + (size_t)p.V * 48;
+        dim3 rgrid(p.tiles_x * p.tiles_y, 1, p.B);
+        if (g32) bevipm::warp_fuse_run_bwd_kernel<float, CELLS, NW><<<rgrid, NW * 32, rsmem, st>>>(p);
+        else bevipm::warp_fuse_run_bwd_kernel<__nv_bfloat16, CELLS, NW><<<rgrid, NW * 32, rsmem, st>>>(p);
+        g_launches.fetch_add(1, std::memory_order_relaxed);
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
     const int c_per_cta = vec ? 128 : 16;
     dim3 grid(p.tiles_x * p.tiles_y, ceil_div(p.C, c_per_cta), p.B);
-    if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "C=%d too large for the backward kernel", p.C);
 #define BEVIPM_LAUNCH_BWD(TG, VEC)                                                                              \
     do {                                                                                                        \
         auto kern = warp_fuse_bwd_kernel<TG, VEC>;                                                              \

@@ -92,6 +92,78 @@ __device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long bas
     cp_async16<CA>(stage + 1536, tap_ptr(base, o.w));
 }
 
+// ---- phase A of the run kernels: one warp builds one row segment's tables, directly in walking order -------------
+// lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view that sees
+// the segment its place in the view list (lane order = views ascending, cells ascending).  sH: the V homographies,
+// rows padded to 4 floats.  MARK_INVALID (backward): out-of-map taps carry offset -1 instead of a stand-in address.
+template <int CELLS, bool WANT_ALL_SEEN, bool MARK_INVALID>
+__device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int i, int j0, int lane, int fsv16, const float* sH,
+                                                 float4* wts, int4* loads, int* ml) {
+    constexpr int GPW = 32 / CELLS;
+    constexpr unsigned CMASK = (1u << CELLS) - 1u;
+    const int gl = lane / CELLS, c = lane - gl * CELLS;
+    const unsigned lt = (1u << lane) - 1u;
+    int nloads = 0, nseen = 0;  // warp-uniform running totals
+    unsigned all_seen = CMASK;  // cells every view sees
+    for (int v0 = 0; v0 < V; v0 += GPW) {
+        const int v = v0 + gl;
+        const bool active = gl < GPW && v < V;
+        const int j = j0 + c;
+        CellTap t;
+        t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
+        if (active && i < p.Hb && j < p.Wb) {
+            float H[9], ix, iy;
+            const float4* hv = reinterpret_cast<const float4*>(sH + 12 * v);
+            const float4 h0 = hv[0], h1 = hv[1], h2 = hv[2];
+            H[0] = h0.x; H[1] = h0.y; H[2] = h0.z; H[3] = h1.x; H[4] = h1.y; H[5] = h1.z; H[6] = h2.x; H[7] = h2.y; H[8] = h2.z;
+            cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
+            t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
+        }
+        const bool seen = t.flags != 0;
+        const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
+        const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
+        const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
+        const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
+        const bool reload = seen && !same;  // the row enters a new 2x2 block here
+        const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
+        const int shift = gl * CELLS;
+        const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
+        const bool lead_seen = active && c == 0 && seen_c != 0;
+        const unsigned lead_b = __ballot_sync(0xffffffffu, lead_seen);
+        if (active) {
+            const int vo = v * fsv16;
+            const bool nf = (t.flags & kNonFinite) != 0;
+            const float qnan = __int_as_float(0x7fc00000);
+            const int tm = t.flags & kTapMask;
+            const int first = tm ? (__ffs(tm) - 1) : 0;
+            // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
+            const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
+            const float w[4] = {t.nw, t.ne, t.sw, t.se};
+            int off[4];
+            float ww[4];
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                const bool ok = (tm >> tap) & 1;
+                off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : (MARK_INVALID ? -1 : safe);
+                ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
+            }
+            wts[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
+            if (reload) loads[nloads + __popc(reload_b & lt)] = make_int4(off[0], off[1], off[2], off[3]);
+            if (c == 0) ml[v] = (int)(seen_c | (reload_c << 16));
+            if (lead_seen) ml[V + nseen + __popc(lead_b & lt)] = v;
+        }
+        nloads += __popc(reload_b);
+        nseen += __popc(lead_b);
+        if (WANT_ALL_SEEN) {
+#pragma unroll
+            for (int gq = 0; gq < GPW; ++gq)
+                if (v0 + gq < V) all_seen &= (seen_b >> (gq * CELLS)) & CMASK;
+        }
+    }
+    if (lane == 0) { ml[2 * V] = nseen; ml[2 * V + 1] = nloads; ml[2 * V + 2] = (int)all_seen; }
+    if (lane < 8) loads[nloads + lane] = make_int4(-1, 0, 0, 0);  // end of list
+}
+
 // ---- TMA form of the ring (template flag TMA): one elected lane hands the copy engine four 512-byte bulk copies per
 // load-list entry (cp.async.bulk global -> shared, completion counted on the stage's mbarrier in bytes); the warp
 // waits on the barrier's phase parity instead of a cp.async group.  No LSU / L1 tag work for the loads at all.
@@ -190,72 +262,8 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
         // ---- phase A: the first warp of every row segment builds the segment's tables, directly in walking order --
         // lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view
         // that sees the segment its place in the view list (lane order = views ascending, cells ascending).
-        if (kk == 0) {
-            float4* wts = seg_wts(r);
-            int4* loads = seg_loads(r);
-            int* ml = seg_meta(r);
-            const int gl = lane / CELLS, c = lane - gl * CELLS;
-            const unsigned lt = (1u << lane) - 1u;
-            int nloads = 0, nseen = 0;  // warp-uniform running totals
-            unsigned all_seen = CMASK;  // cells every view sees
-            for (int v0 = 0; v0 < V; v0 += GPW) {
-                const int v = v0 + gl;
-                const bool active = gl < GPW && v < V;
-                const int j = j0 + c;
-                CellTap t;
-                t.flags = 0; t.x0 = t.y0 = -2; t.off16 = 0; t.nw = t.ne = t.sw = t.se = 0.0f;
-                if (active && i < p.Hb && j < p.Wb) {
-                    float H[9], ix, iy;
-                    const float4* hv = reinterpret_cast<const float4*>(sH + 12 * v);
-                    const float4 h0 = hv[0], h1 = hv[1], h2 = hv[2];
-                    H[0] = h0.x; H[1] = h0.y; H[2] = h0.z; H[3] = h1.x; H[4] = h1.y; H[5] = h1.z; H[6] = h2.x; H[7] = h2.y; H[8] = h2.z;
-                    cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
-                    t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
-                }
-                const bool seen = t.flags != 0;
-                const unsigned seen_b = __ballot_sync(0xffffffffu, seen);
-                const int px0 = __shfl_up_sync(0xffffffffu, t.x0, 1), py0 = __shfl_up_sync(0xffffffffu, t.y0, 1);
-                const bool prev_seen = lane > 0 && ((seen_b >> (lane - 1)) & 1u);
-                const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
-                const bool reload = seen && !same;  // the row enters a new 2x2 block here
-                const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
-                const int shift = gl * CELLS;
-                const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
-                const bool lead_seen = active && c == 0 && seen_c != 0;
-                const unsigned lead_b = __ballot_sync(0xffffffffu, lead_seen);
-                if (active) {
-                    const int vo = v * fsv16;
-                    const bool nf = (t.flags & kNonFinite) != 0;
-                    const float qnan = __int_as_float(0x7fc00000);
-                    const int tm = t.flags & kTapMask;
-                    const int first = tm ? (__ffs(tm) - 1) : 0;
-                    // an in-map tap of this block: where the out-of-map ones (weight 0) are pointed
-                    const int safe = (nf || !tm) ? vo : vo + t.off16 + ((first & 1) ? p.fsx16 : 0) + ((first & 2) ? p.fsy16 : 0);
-                    const float w[4] = {t.nw, t.ne, t.sw, t.se};
-                    int off[4];
-                    float ww[4];
-#pragma unroll
-                    for (int tap = 0; tap < 4; ++tap) {
-                        const bool ok = (tm >> tap) & 1;
-                        off[tap] = ok ? vo + t.off16 + ((tap & 1) ? p.fsx16 : 0) + ((tap & 2) ? p.fsy16 : 0) : safe;
-                        ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
-                    }
-                    wts[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
-                    if (reload) loads[nloads + __popc(reload_b & lt)] = make_int4(off[0], off[1], off[2], off[3]);
-                    if (c == 0) ml[v] = (int)(seen_c | (reload_c << 16));
-                    if (lead_seen) ml[V + nseen + __popc(lead_b & lt)] = v;
-                }
-                nloads += __popc(reload_b);
-                nseen += __popc(lead_b);
-                if (KMODE == KM_MAX) {
-#pragma unroll
-                    for (int gq = 0; gq < GPW; ++gq)
-                        if (v0 + gq < V) all_seen &= (seen_b >> (gq * CELLS)) & CMASK;
-                }
-            }
-            if (lane == 0) { ml[2 * V] = nseen; ml[2 * V + 1] = nloads; ml[2 * V + 2] = (int)all_seen; }
-            if (lane < 8) loads[nloads + lane] = make_int4(-1, 0, 0, 0);  // end of list
-        }
+        if (kk == 0)
+            run_build_tables<CELLS, KMODE == KM_MAX, false>(p, V, i, j0, lane, fsv16, sH, seg_wts(r), seg_loads(r), seg_meta(r));
         if (KSPLIT > 1) __syncthreads();
         else __syncwarp();
 
