@@ -265,6 +265,22 @@ def test_max_fusion_all_three_kernels(dtype, variant):
     assert _same(out, want)
 
 
+@pytest.mark.parametrize("dtype,out_bf16", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)])
+@pytest.mark.parametrize("variant", [0, 1])
+def test_per_view_output_run_and_tile_kernels(dtype, out_bf16, variant):
+    """geometry.py:162-163 on a run-kernel-eligible shape: variant 0 = run kernel (store as you go), 1 = tile kernel.
+    Views that miss cells or whole segments must come out as exact zeros."""
+    feats, K, Rt, xs, ys, img = _rig_case(2, 7, 256, (31, 53), (37, 91), seed=37)
+    f = torch.from_numpy(feats).to(dtype).float().numpy()
+    want = orc.warp_fuse(f, K, Rt, xs, ys, img, "none")
+    assert (want == 0).mean() > 0.05
+    out = _run(f, K, Rt, xs, ys, img, "none", True, dtype=dtype, out_bf16=out_bf16, variant=variant).cpu()
+    if out_bf16:
+        assert torch.equal(out, torch.from_numpy(want).bfloat16())
+    else:
+        assert _same(out.numpy(), want)
+
+
 @pytest.mark.parametrize("views", [1, 2, 9, 16])
 def test_run_kernel_view_counts(views):
     feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)

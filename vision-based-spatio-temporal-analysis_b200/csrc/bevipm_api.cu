@@ -131,7 +131,6 @@ int launch_list(FwdParams p, cudaStream_t st) {
 template <typename TIn>
 bool run_kernel_ok(const FwdParams& p) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
-    if (p.mode != BEVIPM_SUM && p.mode != BEVIPM_MEAN && p.mode != BEVIPM_MAX) return false;
     if (p.V > bevipm::kRunMaxViews) return false;
     if (p.C % (32 * VE)) return false;  // whole 512-byte channel chunks only
     return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
@@ -141,8 +140,8 @@ template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
-    if (!run_kernel_ok<TIn>(p) || (p.mode == BEVIPM_MAX) != (KMODE == bevipm::KM_MAX))
-        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs sum/mean/max, V <= %d, C a multiple of %d, 32-bit tap offsets",
+    if (!run_kernel_ok<TIn>(p) || (p.mode == BEVIPM_MAX) != (KMODE == bevipm::KM_MAX) || (p.mode == BEVIPM_NONE) != (KMODE == bevipm::KM_NONE))
+        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs V <= %d, C a multiple of %d, 32-bit tap offsets, and the variant of the fusion mode",
                     bevipm::kRunMaxViews, 32 * VE);
     p.tiles_x = ceil_div(p.Wb, CELLS);
     p.tiles_y = ceil_div(p.Hb, R);
@@ -190,7 +189,16 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         g_last_variant = 27;
         return launch_list<TIn, TOut, 1, bevipm::KM_MAX, 4, 4>(p, st);
     }
-    if (p.mode == BEVIPM_NONE) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st); }
+    if (p.mode == BEVIPM_NONE) {
+        // per-view maps (geometry.py:163, what ConcatFusion reshapes): the run kernel's store-as-you-go walk where it applies,
+        // the tile kernel otherwise or when the caller forces it (variant 1)
+        if (variant != 1 && run_kernel_ok<TIn>(p)) {
+            g_last_variant = 32;
+            return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_NONE>(p, st);
+        }
+        g_last_variant = 1;
+        return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
+    }
     if (variant == 0) {
         // Defaults, measured on every BASELINE shape (profiles/r01_notes.md):
         //  * whole 512-byte channel chunks, sum/mean, V <= 16: the run kernel (taps re-used in registers along the

@@ -191,7 +191,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // the normal case (wildtrack_loader.py:291-293 reads one calibration per camera).
 // PROBE (timing aid, results are NOT the fusion): 1 = no copies are issued (instruction side alone), 2 = copies and
 // unpack but no blend (memory side alone)
-// KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views, zeros of views that miss a cell included (fusion.py:22).
+// KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views, zeros of views that miss a cell included (fusion.py:22),
+// KM_NONE = the per-view maps GeometryTransformer returns (geometry.py:162-163; what ConcatFusion reshapes): every (view, cell)
+// result is stored as soon as it is blended, zeros where a view does not see a cell; no accumulators at all.
 template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC, bool TMA = false>
 __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
     static_assert(DEPTH >= 2 && DEPTH <= 8, "ring depth");
@@ -199,10 +201,8 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     using VT = VecTraits<TIn>;
     constexpr int VE = VT::VE, P = VT::P;
     constexpr int R = NW / KSPLIT;  // row segments per CTA
-    constexpr int GPW = 32 / CELLS;  // (segment, view) groups one warp projects per pass: a group = CELLS adjacent lanes
-    constexpr unsigned CMASK = (1u << CELLS) - 1u;
     constexpr int NT = NW * 32;
-    constexpr int ILP = (MAXREG <= 128 && P > 2 && CELLS >= 8) ? 2 : P;  // at 128 registers there is room for two chains in flight, not four
+    constexpr int ILP = (KMODE == KM_NONE) ? P : ((MAXREG <= 128 && P > 2 && CELLS >= 8) ? 2 : P);  // at 128 registers there is room for two chains in flight, not four
     static_assert(CELLS >= 2 && CELLS <= 16, "cells per segment");
     static_assert(NW % KSPLIT == 0 && (KSPLIT == 1 || KSPLIT == 2 || KSPLIT == 4), "warps per row segment");
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -342,6 +342,9 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
             for (int c = 0; c < CELLS; ++c)
 #pragma unroll
                 for (int q = 0; q < P; ++q) acc[c][q] = (KMODE == KM_MAX) ? make_float2(-INFINITY, -INFINITY) : make_float2(0.0f, 0.0f);
+            // KM_NONE: this item's 16 bytes of view 0, cell 0 in the per-view output
+            TOut* ovb = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_c) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
+                        (k_c * 32 + lane) * VE;
 
             if (nviews > 0) {
                 float2 cur[4][P];
@@ -421,6 +424,14 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                                 for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[2][q0 + q], make_float2(w.z, w.z), sv[q]);
 #pragma unroll
                                 for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
+                                if constexpr (KMODE == KM_NONE) {  // geometry.py:162: the view's map, zero where it does not see the cell
+                                    if (j0 + c < p.Wb) {
+                                        float2 z[P];
+#pragma unroll
+                                        for (int q = 0; q < P; ++q) z[q] = seen ? sv[q] : make_float2(0.0f, 0.0f);
+                                        store_pairs<TOut, P>(ovb + (long long)v * p.os_v + (long long)c * p.os_x, z);
+                                    }
+                                } else
 #pragma unroll
                                 for (int q = 0; q < ILP; ++q)
                                     if (seen) {
@@ -447,6 +458,21 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 prime(lbase);
             }
 
+            if constexpr (KMODE == KM_NONE) {
+                // views that do not see the segment at all: their part of the per-view output is zero
+                float2 z[P];
+#pragma unroll
+                for (int q = 0; q < P; ++q) z[q] = make_float2(0.0f, 0.0f);
+                TOut* ob0 = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_this) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
+                            (k_this * 32 + lane) * VE;
+                for (int v = 0; v < V; ++v) {
+                    if ((lds4i(s_meta + 4 * v) & 0xffff) != 0) continue;
+#pragma unroll
+                    for (int c = 0; c < CELLS; ++c)
+                        if (j0 + c < p.Wb) store_pairs<TOut, P>(ob0 + (long long)v * p.os_v + (long long)c * p.os_x, z);
+                }
+                continue;
+            }
             // ---- epilogue: mean division (IEEE quotient) and one 16-byte store per cell ---------------------------
             if constexpr (KMODE == KM_MAX) {
                 // a view that misses the cell contributes its zero padding to the maximum (geometry.py:94 + fusion.py:22)
