@@ -325,6 +325,32 @@ def run_ours(args, wl):
     ms_per_step = ms_total / args.steps
     value = (1 if views_mode else world) * B * args.steps / (ms_total * 1e-3)
 
+    # ---- the same launch in per-view (concat) mode: what BEVNet's GeometryTransformer + ConcatFusion produce ------
+    concat = None
+    if world == 1 and not views_mode:
+        try:
+            n_pv = max(3, min(args.steps, 20))
+            for _ in range(3):
+                pv = ops.warp_fuse(feats, Kd, Rd, xd, yd, img[0], img[1], _lib.NONE, out_bf16, args.variant)
+            torch.cuda.synchronize(dev)
+            p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            p0.record()
+            for _ in range(n_pv):
+                pv = ops.warp_fuse(feats, Kd, Rd, xd, yd, img[0], img[1], _lib.NONE, out_bf16, args.variant)
+            p1.record()
+            torch.cuda.synchronize(dev)
+            pv_ms = p0.elapsed_time(p1) / n_pv
+            pv_alg = rig.algorithmic_bytes(ix[0].cpu().numpy(), iy[0].cpu().numpy(), wl.feat_hw, C, wl.feat_elem_bytes,
+                                           wl.out_elem_bytes, per_view_out=True)["b_alg"] * B
+            concat = {"ms_per_step": pv_ms, "frames_per_s": B / (pv_ms * 1e-3), "algorithmic_bytes_per_launch": pv_alg,
+                      "achieved_gbs": pv_alg / (pv_ms * 1e-3) / 1e9, "steps": n_pv,
+                      "kernel": _lib.variant_name(int(_lib.load().bevipm_last_variant())),
+                      "note": "fusion mode none/concat: V per-view BEV maps written instead of one (informational; not the headline metric)"}
+            del pv
+            torch.cuda.empty_cache()
+        except RuntimeError as e:   # e.g. out of memory on a smaller device: the headline numbers stand
+            concat = {"error": str(e)[:200]}
+
     # ---- end to end through the host-buffer entry of the C ABI ---------------------------------
     e2e = None
     if not args.no_e2e and not views_mode:
@@ -380,6 +406,10 @@ def run_ours(args, wl):
         }
         if e2e:
             line["e2e"] = e2e
+        if concat:
+            if "achieved_gbs" in concat:
+                concat["frac"] = concat["achieved_gbs"] / peak
+            line["concat_mode"] = concat
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_port_frames_per_s(wl)
         print(json.dumps(line), flush=True)
