@@ -212,6 +212,11 @@ def test_run_kernel_frame_runs_share_tables_only_when_calibration_repeats(monkey
     outb = _run(fb, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, "sum", True, dtype=torch.bfloat16,
                 variant=variant).cpu().numpy()
     assert _same(outb, wantb)
+    if variant == 33:   # the other fusion modes of the run kernel walk the same shared tables (default dispatch)
+        for mode in ("max", "none"):
+            wantm = orc.warp_fuse(fb, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, mode)
+            outm = _run(fb, K, Rt, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, mode, True, dtype=torch.bfloat16).cpu().numpy()
+            assert _same(outm, wantm), mode
 
 
 def test_run_kernel_non_finite_features_take_the_exact_division():
