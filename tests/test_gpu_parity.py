@@ -286,6 +286,23 @@ def test_per_view_output_run_and_tile_kernels(dtype, out_bf16, variant):
         assert _same(out.numpy(), want)
 
 
+@pytest.mark.parametrize("variant", [0, 31, 33, 35, 37])
+@pytest.mark.parametrize("C,dtype", [(136, torch.float32), (64, torch.float32), (4, torch.float32), (264, torch.bfloat16), (8, torch.bfloat16)])
+@pytest.mark.parametrize("mode", ["mean", "max", "none"])
+def test_run_kernel_partial_channel_chunks(variant, C, dtype, mode):
+    """C is not a multiple of one 512-byte chunk (the reference's sanity config has C = 64): the spare lanes of the
+    last chunk re-read valid channels and store nothing."""
+    if mode != "mean" and variant != 0:
+        pytest.skip("forced run-kernel variants are the sum/mean instantiations")
+    feats, K, Rt, xs, ys, img = _rig_case(2, 5, C, (31, 53), (37, 91), seed=41)
+    f = torch.from_numpy(feats).to(dtype).float().numpy()
+    want = orc.warp_fuse(f, K, Rt, xs, ys, img, mode)
+    out = _run(f, K, Rt, xs, ys, img, mode, True, dtype=dtype, variant=variant).cpu().numpy()
+    assert _same(out, want)
+    from bevipm import _lib
+    assert 30 <= int(_lib.load().bevipm_last_variant()) <= 39   # really the run kernel
+
+
 @pytest.mark.parametrize("views", [1, 2, 9, 16])
 def test_run_kernel_view_counts(views):
     feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)

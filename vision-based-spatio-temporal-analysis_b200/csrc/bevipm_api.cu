@@ -132,7 +132,6 @@ template <typename TIn>
 bool run_kernel_ok(const FwdParams& p) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     if (p.V > bevipm::kRunMaxViews) return false;
-    if (p.C % (32 * VE)) return false;  // whole 512-byte channel chunks only
     return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
 }
 
@@ -140,9 +139,9 @@ template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
+    if (TMA && p.C % (32 * VE)) return fail(BEVIPM_ERR_UNSUPPORTED, "the TMA ring copies whole 512-byte chunks: C must be a multiple of %d", 32 * VE);
     if (!run_kernel_ok<TIn>(p) || (p.mode == BEVIPM_MAX) != (KMODE == bevipm::KM_MAX) || (p.mode == BEVIPM_NONE) != (KMODE == bevipm::KM_NONE))
-        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs V <= %d, C a multiple of %d, 32-bit tap offsets, and the variant of the fusion mode",
-                    bevipm::kRunMaxViews, 32 * VE);
+        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs V <= %d, 32-bit tap offsets, and the variant of the fusion mode", bevipm::kRunMaxViews);
     p.tiles_x = ceil_div(p.Wb, CELLS);
     p.tiles_y = ceil_div(p.Hb, R);
     p.fsy16 = (int)(p.fs_y / VE);
@@ -237,7 +236,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
         // run kernel <cells per segment, warps per CTA, warps per segment, register cap, ring depth, .ca>:
         // 32 = fp32 default, 33 = bf16 default; the others are the sweep points quoted in profiles/r01_notes.md
-        case 30: return launch_run<TIn, TOut, 8, 4, 4, 128, 5, false>(p, st);
+        case 30: return launch_run<TIn, TOut, 4, 4, 1, 96, 4, false>(p, st);
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
         case 32: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);

@@ -224,7 +224,8 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     const int fsv16 = (int)(p.fs_v / VE);
     const int r = warp / KSPLIT, kk = warp - r * KSPLIT;
     const int i = i0 + r;
-    const int chunks = p.C / (32 * VE);
+    const int chunks = (p.C + 32 * VE - 1) / (32 * VE);  // the last one may be partial: its spare lanes re-read the last
+    const int last_vec = p.C / VE - 1;                    // valid 16 bytes of the texel and store nothing
     const float Vf = (float)V;
     const uint32_t s_wts = (uint32_t)__cvta_generic_to_shared(seg_wts(r));
     const uint32_t s_loads = (uint32_t)__cvta_generic_to_shared(seg_loads(r));
@@ -302,7 +303,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
         // lane base of an item's chunk
         auto item_base = [&](int fi, int k) {
             return reinterpret_cast<unsigned long long>(
-                reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(p.feats) + (long long)(b_run + fi) * p.fs_b) + (k * 32 + lane));
+                reinterpret_cast<const uint4*>(reinterpret_cast<const TIn*>(p.feats) + (long long)(b_run + fi) * p.fs_b) + min(k * 32 + lane, last_vec));
         };
         // entries 0 .. DEPTH-2 of the load list start flying: one commit group per entry (past the end of the list
         // the entries carry x = -1: nothing is copied, the group is empty).  Called before the first item and, for
@@ -342,6 +343,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
             for (int c = 0; c < CELLS; ++c)
 #pragma unroll
                 for (int q = 0; q < P; ++q) acc[c][q] = (KMODE == KM_MAX) ? make_float2(-INFINITY, -INFINITY) : make_float2(0.0f, 0.0f);
+            const bool lok = k_c * 32 + lane <= last_vec;  // this lane holds real channels of this item's chunk
             // KM_NONE: this item's 16 bytes of view 0, cell 0 in the per-view output
             TOut* ovb = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_c) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
                         (k_c * 32 + lane) * VE;
@@ -425,7 +427,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
 #pragma unroll
                                 for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
                                 if constexpr (KMODE == KM_NONE) {  // geometry.py:162: the view's map, zero where it does not see the cell
-                                    if (j0 + c < p.Wb) {
+                                    if (lok && j0 + c < p.Wb) {
                                         float2 z[P];
 #pragma unroll
                                         for (int q = 0; q < P; ++q) z[q] = seen ? sv[q] : make_float2(0.0f, 0.0f);
@@ -469,7 +471,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                     if ((lds4i(s_meta + 4 * v) & 0xffff) != 0) continue;
 #pragma unroll
                     for (int c = 0; c < CELLS; ++c)
-                        if (j0 + c < p.Wb) store_pairs<TOut, P>(ob0 + (long long)v * p.os_v + (long long)c * p.os_x, z);
+                        if (lok && j0 + c < p.Wb) store_pairs<TOut, P>(ob0 + (long long)v * p.os_v + (long long)c * p.os_x, z);
                 }
                 continue;
             }
@@ -525,6 +527,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
             }
             TOut* oc = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_this) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
                        (k_this * 32 + lane) * VE;
+            if (!lok) continue;
             if (j0 + CELLS <= p.Wb) {
 #pragma unroll
                 for (int c = 0; c < CELLS; ++c) {
