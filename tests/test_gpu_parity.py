@@ -303,7 +303,7 @@ def test_run_kernel_partial_channel_chunks(variant, C, dtype, mode):
     assert 30 <= int(_lib.load().bevipm_last_variant()) <= 39   # really the run kernel
 
 
-@pytest.mark.parametrize("views", [1, 2, 9, 16])
+@pytest.mark.parametrize("views", [1, 2, 9, 16, 17, 32])
 def test_run_kernel_view_counts(views):
     feats, K, Rt, xs, ys, img = _rig_case(1, views, 128, (20, 33), (19, 45), seed=10 + views)
     want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")

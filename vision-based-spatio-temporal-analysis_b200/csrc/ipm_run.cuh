@@ -33,7 +33,7 @@
 
 namespace bevipm {
 
-constexpr int kRunMaxViews = 16;
+constexpr int kRunMaxViews = 32;
 
 // shared-memory bytes of the R row segments' tables, rounded up so that the rings behind them start on a 128-byte
 // boundary: a warp's 512-byte ring access that straddles bank rows costs a fifth wavefront (measured: +14 % on c1)
