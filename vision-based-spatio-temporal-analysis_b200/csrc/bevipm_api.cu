@@ -175,10 +175,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
                                (long long)(p.Hf + 2) * (p.fs_y / bevipm::VecTraits<TIn>::VE) +
                                (long long)(p.Wf + 2) * (p.fs_x / bevipm::VecTraits<TIn>::VE);
         if (variant == 1 || span > 0x7fffffffLL) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st); }
-        // measured (tools/bench_modes.py, run vs list): c1 0.102 / 0.091 ms, c2 0.785 / 0.786, c3 0.278 / 0.356 -> the run
-        // kernel's max walk except for fp32 texels of 2 KB and more
-        if (variant != 21 && run_kernel_ok<TIn>(p) && !(sizeof(TIn) == 4 && (long long)p.C * 4 >= 2048)) {
-            if (sizeof(TIn) == 4) { g_last_variant = 32; return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_MAX>(p, st); }
+        if (variant != 21 && run_kernel_ok<TIn>(p)) {  // the run kernel's max walk
             g_last_variant = 33;
             return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, bevipm::KM_MAX>(p, st);
         }
