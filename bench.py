@@ -52,6 +52,7 @@ def parse_args():
     ap.add_argument("--variant", type=int, default=0, help="force a fused-kernel variant (sweeps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-concat", action="store_true", help="skip the informational per-view (concat) mode block")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
     ap.add_argument("--shard", default="frames", choices=["frames", "views"],
                     help="N>1: frames = every rank runs its own batch (weak scaling, no collective); "
@@ -327,7 +328,7 @@ def run_ours(args, wl):
 
     # ---- the same launch in per-view (concat) mode: what BEVNet's GeometryTransformer + ConcatFusion produce ------
     concat = None
-    if world == 1 and not views_mode:
+    if world == 1 and not views_mode and not args.no_concat:
         try:
             n_pv = max(3, min(args.steps, 20))
             for _ in range(3):
