@@ -48,6 +48,12 @@ enum bevipm_dtype { BEVIPM_F32 = 0, BEVIPM_BF16 = 1 };
  * [B,V,C,Hb,Wb], i.e. GeometryTransformer's own output, which ConcatFusion merely reshapes. */
 enum bevipm_mode { BEVIPM_SUM = 0, BEVIPM_MEAN = 1, BEVIPM_MAX = 2, BEVIPM_NONE = 3 };
 
+/* bevipm_desc.flags: sample positions of the reference's kornia branch (geometry.py:124-141: kornia's
+ * warp_perspective normalises pixel grids with (size-1) and samples with align_corners=False, so a source pixel p is
+ * read at p*size/(size-1) - 0.5; the caller passes BEV cell CORNERS x_min + j*res_x in xs/ys, which is where that
+ * branch puts BEV pixel j).  From kornia's published algorithm; kornia is not installed here: parity unpinned. */
+#define BEVIPM_FLAG_KORNIA_GEOMETRY 1
+
 typedef struct bevipm_desc {
     int32_t B, V, C;        /* frames, views (cameras), channels */
     int32_t Hf, Wf;         /* feature-map size */
@@ -57,7 +63,7 @@ typedef struct bevipm_desc {
     int32_t in_dtype;       /* bevipm_dtype of feats (fwd) / grad_feats is always f32 (bwd) */
     int32_t out_dtype;      /* bevipm_dtype of out (fwd) / grad_out (bwd) */
     int32_t variant;        /* 0 = library picks the kernel; >0 forces one, for sweeps */
-    int32_t reserved;
+    int32_t flags;          /* BEVIPM_FLAG_* bits; 0 = the reference's grid_sample geometry */
     int64_t fs_b, fs_v, fs_c, fs_y, fs_x; /* feats[b,v,c,y,x] strides; fs_c == 1 is the NHWC fast path */
     int64_t os_b, os_v, os_c, os_y, os_x; /* out[b,(v,)c,i,j] strides; os_v is read only for NONE */
 } bevipm_desc;

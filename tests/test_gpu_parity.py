@@ -584,3 +584,36 @@ def test_mean_division_is_ieee(variant):
     assert torch.equal(torch.isnan(m), torch.isnan(want))
     assert torch.equal(m[~torch.isnan(m)], want[~torch.isnan(want)])
     assert bool(torch.isinf(m).any()) and bool(torch.isnan(m).any())
+
+
+# ---- kornia-compatible geometry (compat mode, parity unpinned: kornia is not installed anywhere we can run) --------
+
+@pytest.mark.parametrize("fusion", ["none", "mean"])
+def test_emulate_kornia_matches_from_spec_restatement(fusion):
+    """bevipm's emulate_kornia=True against oracle/kornia_chain.py (kornia's published warp_perspective algorithm over
+    the M of geometry.py:126-133).  Two different fp32 routes to the same sample positions (ours: H, then p*size/(size-1)
+    - 0.5; kornia's: normalised homographies and a matrix inverse), so the check is a tolerance on smooth features."""
+    import bevipm
+    from bevipm import rig
+    from oracle import kornia_chain
+    B, V, C, fhw, bhw = 1, 4, 8, (34, 60), (30, 90)
+    K, Rt = rig.look_at_rig(V, 5)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, fhw[0]), torch.linspace(0, 1, fhw[1]), indexing="ij")
+    base = torch.stack([torch.sin(3 * xx + c) * torch.cos(2 * yy - 0.3 * c) for c in range(C)])      # smooth maps
+    feats = torch.stack([base * (1 + 0.1 * v) for v in range(V)])[None].contiguous()
+    want = kornia_chain.warp_views(feats, K[None], Rt[None], bhw, rig.WILDTRACK_BOUNDS, rig.WILDTRACK_IMG_SIZE)
+    if fusion == "mean":
+        want = want.mean(dim=1)
+    mod = bevipm.FusedIPM(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS, fusion=fusion if fusion != "none" else "concat",
+                          warp_impl="kornia", emulate_kornia=True).to(DEV)
+    out = mod(feats.to(DEV), K[None].to(DEV), Rt[None].to(DEV), img_size=rig.WILDTRACK_IMG_SIZE).cpu()
+    out = out.reshape(want.shape)
+    # interior agreement; a cell whose sample sits within ~1e-3 px of the map border may flip a tap in or out
+    diff = (out - want).abs()
+    assert float(diff.median()) <= 1e-5
+    assert float((diff > 2e-3 * float(want.abs().max())).float().mean()) <= 2e-3
+    # and it really is a different geometry from the grid_sample branch (half a BEV cell + the (size-1) scaling)
+    ref = bevipm.FusedIPM(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS, fusion=fusion if fusion != "none" else "concat",
+                          warp_impl="kornia").to(DEV)(feats.to(DEV), K[None].to(DEV), Rt[None].to(DEV),
+                                                       img_size=rig.WILDTRACK_IMG_SIZE).cpu().reshape(want.shape)
+    assert float((ref - want).abs().median()) > 10 * float(diff.median()) + 1e-6

@@ -12,6 +12,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(__import__("os").environ.get("BEVIPM_LIB", PKG / "libbevipm.so"))  # BEVIPM_LIB: A/B of two builds (development aid)
 
 F32, BF16 = 0, 1
+FLAG_KORNIA_GEOMETRY = 1
 SUM, MEAN, MAX, NONE = 0, 1, 2, 3
 MODES = {"sum": SUM, "mean": MEAN, "max": MAX, "none": NONE, "concat": NONE}
 
@@ -20,7 +21,7 @@ class Desc(ctypes.Structure):
     """struct bevipm_desc (include/bevipm.h)."""
     _fields_ = [(n, ctypes.c_int32) for n in
                 ("B", "V", "C", "Hf", "Wf", "Hb", "Wb", "img_h", "img_w", "mode", "in_dtype", "out_dtype",
-                 "variant", "reserved")] + \
+                 "variant", "flags")] + \
                [(n, ctypes.c_int64) for n in
                 ("fs_b", "fs_v", "fs_c", "fs_y", "fs_x", "os_b", "os_v", "os_c", "os_y", "os_x")]
 

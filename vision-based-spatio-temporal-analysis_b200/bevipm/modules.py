@@ -104,7 +104,19 @@ class _IPMBase(nn.Module):
                                g[:, 0, 1].to(device=device, dtype=torch.float32).contiguous())
         return self._axes[key]
 
-    def _run(self, feats, intrinsics, extrinsics, img_size, mode: int, out_bf16: bool, variant: int, layout: str):
+    def _corner_axes(self, device):
+        """BEV cell CORNERS x_min + j*res_x, y_min + i*res_y: where the reference's kornia branch puts BEV pixel (i, j)
+        (geometry.py:129-131, A_w2bev maps world -> BEV pixel without a half-cell offset)."""
+        key = "corner:" + str(device)
+        if key not in self._axes:
+            min_x, _, min_y, _ = self.bounds
+            xs = (torch.arange(self.bev_w, dtype=torch.float64) * self.res_x + min_x).to(torch.float32)
+            ys = (torch.arange(self.bev_h, dtype=torch.float64) * self.res_y + min_y).to(torch.float32)
+            self._axes[key] = (xs.to(device).contiguous(), ys.to(device).contiguous())
+        return self._axes[key]
+
+    def _run(self, feats, intrinsics, extrinsics, img_size, mode: int, out_bf16: bool, variant: int, layout: str,
+             kornia_geometry: bool = False):
         if feats.dim() != 5:
             raise ValueError("feats must be [B,V,C,Hf,Wf]")
         if not feats.is_cuda:
@@ -113,7 +125,9 @@ class _IPMBase(nn.Module):
         if feats.dtype == torch.float16:
             feats = feats.float()  # grid_sampler's autocast policy is fp32 (the reference under train.py:239)
         K, Rt = pack_calibration(intrinsics, extrinsics, B, V, feats.device)
-        xs, ys = self._ground_axes(feats.device)
+        xs, ys = self._corner_axes(feats.device) if kornia_geometry else self._ground_axes(feats.device)
+        if kornia_geometry:
+            mode = mode | (_lib.FLAG_KORNIA_GEOMETRY << 8)
         if layout == "channels_last" or (layout == "auto" and feats.shape[2] % (4 if feats.dtype == torch.float32 else 8) == 0):
             feats = ops.to_channels_last5(feats)
         H_img, W_img = img_size
@@ -123,11 +137,16 @@ class _IPMBase(nn.Module):
 class GeometryTransformer(_IPMBase):
     """Per-view IPM warp, drop-in for geometry.py:12-163 (grid_sample semantics)."""
 
-    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, warp_impl: str = "grid_sample", layout: str = "keep"):
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, warp_impl: str = "grid_sample", layout: str = "keep",
+                 emulate_kornia: bool = False):
         super().__init__(bev_h, bev_w, bev_bounds)
         # geometry.py:20 -- both names are accepted; 'kornia' executes the grid_sample branch in any
-        # environment without kornia (this image), which is the behaviour mirrored here
+        # environment without kornia (this image), which is the behaviour mirrored here.  emulate_kornia=True
+        # (with warp_impl='kornia') instead reproduces the sample positions of the kornia branch
+        # (geometry.py:124-141) for users whose reference runs WITH kornia: BEV pixel j at the cell corner,
+        # source pixel p read at p*size/(size-1) - 0.5.  From kornia's published algorithm: parity unpinned.
         self.warp_impl = warp_impl if warp_impl in ("grid_sample", "kornia") else "grid_sample"
+        self.emulate_kornia = bool(emulate_kornia) and self.warp_impl == "kornia"
         self.layout = layout
         self._grid_cache = {}
 
@@ -157,7 +176,7 @@ class GeometryTransformer(_IPMBase):
     def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
                 img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
         """feats [B,V,C,Hf,Wf] -> [B,V,C,Hb,Wb] float32 (geometry.py:94: fp32 whatever the input)."""
-        return self._run(feats, intrinsics, extrinsics, img_size, _lib.NONE, False, 0, self.layout)
+        return self._run(feats, intrinsics, extrinsics, img_size, _lib.NONE, False, 0, self.layout, self.emulate_kornia)
 
 
 class FusedIPM(_IPMBase):
@@ -167,13 +186,14 @@ class FusedIPM(_IPMBase):
 
     def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, fusion: str = "mean",
                  warp_impl: str = "grid_sample", out_dtype: torch.dtype = torch.float32,
-                 layout: str = "auto", variant: int = 0):
+                 layout: str = "auto", variant: int = 0, emulate_kornia: bool = False):
         super().__init__(bev_h, bev_w, bev_bounds)
         assert fusion in ("sum", "mean", "max", "concat", "none")
         assert out_dtype in (torch.float32, torch.bfloat16)
         assert layout in ("auto", "keep", "channels_last")
         self.fusion = fusion
         self.warp_impl = warp_impl if warp_impl in ("grid_sample", "kornia") else "grid_sample"
+        self.emulate_kornia = bool(emulate_kornia) and self.warp_impl == "kornia"   # see GeometryTransformer
         self.out_dtype = out_dtype
         self.layout = layout   # "auto": NCHW-contiguous features go through our transpose pre-pass
         self.variant = variant
@@ -181,7 +201,7 @@ class FusedIPM(_IPMBase):
     def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
                 img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
         out = self._run(feats, intrinsics, extrinsics, img_size, _lib.MODES[self.fusion],
-                        self.out_dtype == torch.bfloat16, self.variant, self.layout)
+                        self.out_dtype == torch.bfloat16, self.variant, self.layout, self.emulate_kornia)
         if self.fusion == "concat":
             B, V, C, Hb, Wb = out.shape
             return out.reshape(B, V * C, Hb, Wb)   # fusion.py:45-46, channel index v*C + c

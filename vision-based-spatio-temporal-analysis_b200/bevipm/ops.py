@@ -25,13 +25,14 @@ def _ptr(t: torch.Tensor) -> ctypes.c_void_p:
     return ctypes.c_void_p(t.data_ptr())
 
 
-def _fill_desc(feat_shape, feat_strides, out_strides, bev_hw, img_hw, mode, in_dt, out_dt, variant) -> Desc:
+def _fill_desc(feat_shape, feat_strides, out_strides, bev_hw, img_hw, mode, in_dt, out_dt, variant, flags=0) -> Desc:
     B, V, C, Hf, Wf = feat_shape
     d = Desc()
     d.B, d.V, d.C, d.Hf, d.Wf = B, V, C, Hf, Wf
     d.Hb, d.Wb = bev_hw
     d.img_h, d.img_w = img_hw
     d.mode, d.in_dtype, d.out_dtype, d.variant = mode, in_dt, out_dt, variant
+    d.flags = flags
     d.fs_b, d.fs_v, d.fs_c, d.fs_y, d.fs_x = feat_strides
     d.os_b, d.os_v, d.os_c, d.os_y, d.os_x = out_strides
     return d
@@ -81,13 +82,14 @@ def warp_fuse(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs: torc
         raise TypeError(f"feats dtype {feats.dtype} is not supported (float32 / bfloat16)")
     _check_calib(feats, K, Rt34, xs, ys)
     L = _lib.load()
+    mode, flags = mode & 0xff, mode >> 8   # bevipm_desc.flags ride in the high bits of `mode` (see modules._IPMBase._run)
     per_view = mode == _lib.NONE
     Hb, Wb = ys.numel(), xs.numel()
     out_dtype = torch.bfloat16 if out_bf16 else torch.float32
     with torch.cuda.device(feats.device):
         out = _alloc_out(feats, Hb, Wb, per_view, out_dtype, _is_channels_last5(feats))
         d = _fill_desc(feats.shape, feats.stride(), _out_strides5(out, per_view), (Hb, Wb), (img_h, img_w), mode,
-                       _DT[feats.dtype], _DT[out_dtype], variant)
+                       _DT[feats.dtype], _DT[out_dtype], variant, flags)
         _lib.check(L.bevipm_warp_fuse_fwd(ctypes.byref(d), _ptr(feats), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys),
                                           _ptr(out), ctypes.c_void_p(_stream_ptr(feats.device))))
     return out
@@ -98,7 +100,7 @@ def _(feats, K, Rt34, xs, ys, img_h, img_w, mode, out_bf16, variant):
     B, V, C = feats.shape[:3]
     Hb, Wb = ys.numel(), xs.numel()
     dt = torch.bfloat16 if out_bf16 else torch.float32
-    shape = (B, V, C, Hb, Wb) if mode == _lib.NONE else (B, C, Hb, Wb)
+    shape = (B, V, C, Hb, Wb) if (mode & 0xff) == _lib.NONE else (B, C, Hb, Wb)
     return feats.new_empty(shape, dtype=dt)
 
 
@@ -108,6 +110,7 @@ def warp_fuse_bwd(grad_out: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, x
     """fp32 gradient w.r.t. the features (scatter of the forward taps; train.py:243 reaches it)."""
     L = _lib.load()
     B, V, C, Hf, Wf = feat_shape
+    mode, flags = mode & 0xff, mode >> 8
     per_view = mode == _lib.NONE
     if grad_out.dtype not in _DT:
         grad_out = grad_out.float()
@@ -123,7 +126,7 @@ def warp_fuse_bwd(grad_out: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, x
         else:
             g = torch.zeros((B, V, C, Hf, Wf), device=grad_out.device, dtype=torch.float32)
         d = _fill_desc(feat_shape, g.stride(), _out_strides5(grad_out, per_view), (ys.numel(), xs.numel()),
-                       (img_h, img_w), mode, _lib.F32, _DT[grad_out.dtype], 0)
+                       (img_h, img_w), mode, _lib.F32, _DT[grad_out.dtype], 0, flags)
         _lib.check(L.bevipm_warp_fuse_bwd(ctypes.byref(d), _ptr(grad_out), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys),
                                           _ptr(g), ctypes.c_void_p(_stream_ptr(grad_out.device))))
     return g

@@ -69,6 +69,11 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
     p.tiles_x = p.tiles_y = p.chunks = p.chunks_per_cta = p.chunk_groups = p.total_tiles = 0;
     p.fsy16 = p.fsx16 = 0;
     p.rcpV = 0.0f;
+    p.kx = p.ky = 0.0f;
+    if (d->flags & BEVIPM_FLAG_KORNIA_GEOMETRY) {
+        p.kx = d->Wf > 1 ? (float)((double)d->Wf / (double)(d->Wf - 1)) : 1.0f;
+        p.ky = d->Hf > 1 ? (float)((double)d->Hf / (double)(d->Hf - 1)) : 1.0f;
+    }
     return p;
 }
 

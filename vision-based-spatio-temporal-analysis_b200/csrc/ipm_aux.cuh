@@ -156,7 +156,7 @@ __global__ void sample_coords_kernel(const FwdParams p, float* __restrict__ ix, 
     if (cell >= p.Hb * p.Wb) return;
     const int i = cell / p.Wb, j = cell - i * p.Wb;
     float x, y;
-    cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y);
+    cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y, p.kx, p.ky);
     ix[(long long)bv * p.Hb * p.Wb + cell] = x;
     iy[(long long)bv * p.Hb * p.Wb + cell] = y;
 }
@@ -176,7 +176,7 @@ __global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span) 
     if (cell < p.Hb * p.Wb) {
         const int i = cell / p.Wb, j = cell - i * p.Wb;
         float x, y;
-        cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y);
+        cell_coord(H, p.xs[j], p.ys[i], p.sw, p.sh, (float)p.Wf, (float)p.Hf, x, y, p.kx, p.ky);
         const CellTap t = make_tap(x, y, p.Wf, p.Hf);
         const int tm = t.flags & kTapMask;
 #pragma unroll

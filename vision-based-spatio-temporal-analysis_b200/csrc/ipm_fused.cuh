@@ -45,6 +45,7 @@ struct FwdParams {
     int total_tiles;     // fused kernel: tiles_x * tiles_y * chunk_groups * B
     int fsy16, fsx16;    // fs_y, fs_x in 16-byte units (fast path)
     float rcpV;          // RN(1 / V) for the exact mean division
+    float kx, ky;        // 0 = reference grid_sample geometry; Wf/(Wf-1), Hf/(Hf-1) = kornia-compatible sample positions
 };
 
 enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2, KM_PROBE = 3 /* timing probe: loads only, no blend */ };
@@ -146,7 +147,7 @@ __device__ __forceinline__ void project_patch(const FwdParams& p, int b, int i0,
         CellTap t;
         if (i < p.Hb && j < p.Wb) {
             float ix, iy;
-            cell_coord(sH + 9 * v, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, Wm, Hm, ix, iy);
+            cell_coord(sH + 9 * v, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, Wm, Hm, ix, iy, p.kx, p.ky);
             t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
         } else {
             t.x0 = t.y0 = -2; t.nw = t.ne = t.sw = t.se = 0.0f; t.flags = 0; t.off16 = 0;

@@ -41,8 +41,11 @@ __device__ __forceinline__ void homography(const float* __restrict__ K, const fl
 
 // geometry.py:144-158 + grid_sampler's align_corners=False un-normalisation:
 // world ground point (x, y) -> feature-pixel sample position (ix, iy).
+// kx, ky = 0: the reference's grid_sample branch (the chain below).  kx = Wf/(Wf-1), ky = Hf/(Hf-1): the sample
+// position of the reference's kornia branch (geometry.py:124-141 through kornia's warp_perspective: pixel grid
+// normalised with (size-1), sampled with align_corners=False) -- a from-spec compatibility mode, parity unpinned.
 __device__ __forceinline__ void cell_coord(const float* H, float x, float y, float sw, float sh,
-                                           float Wf, float Hf, float& ix, float& iy) {
+                                           float Wf, float Hf, float& ix, float& iy, float kx = 0.0f, float ky = 0.0f) {
     // :145  uvw = H @ [x; y; 1]
     const float r0 = __fmaf_rn(H[2], 1.0f, __fmaf_rn(H[1], y, __fmul_rn(H[0], x)));
     const float r1 = __fmaf_rn(H[5], 1.0f, __fmaf_rn(H[4], y, __fmul_rn(H[3], x)));
@@ -55,6 +58,11 @@ __device__ __forceinline__ void cell_coord(const float* H, float x, float y, flo
     // :151-155  image px -> feature px
     const float fx = __fmul_rn(u, sw);
     const float fy = __fmul_rn(v, sh);
+    if (kx != 0.0f) {  // kornia: source pixel p -> 2p/(size-1)-1 -> grid_sample(align_corners=False): p * size/(size-1) - 0.5
+        ix = __fmaf_rn(fx, kx, -0.5f);
+        iy = __fmaf_rn(fy, ky, -0.5f);
+        return;
+    }
     // :156-158  (p + 0.5) / size * 2 - 1, four separately rounded ops, true division
     const float nx = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(fx, 0.5f), Wf), 2.0f), 1.0f);
     const float ny = __fsub_rn(__fmul_rn(__fdiv_rn(__fadd_rn(fy, 0.5f), Hf), 2.0f), 1.0f);

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) warp_fuse_list_kernel(const
         if (e < E && j0 + q < p.Wb) {
             float H[9], ix, iy;
             homography(p.K + 9 * (b * V + v), p.Rt + 12 * (b * V + v), H);
-            cell_coord(H, __ldg(p.xs + j0 + q), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
+            cell_coord(H, __ldg(p.xs + j0 + q), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy, p.kx, p.ky);
             t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
             in_grid = true;
         }

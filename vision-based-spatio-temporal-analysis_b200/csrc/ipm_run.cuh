@@ -116,7 +116,7 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
             const float4* hv = reinterpret_cast<const float4*>(sH + 12 * v);
             const float4 h0 = hv[0], h1 = hv[1], h2 = hv[2];
             H[0] = h0.x; H[1] = h0.y; H[2] = h0.z; H[3] = h1.x; H[4] = h1.y; H[5] = h1.z; H[6] = h2.x; H[7] = h2.y; H[8] = h2.z;
-            cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy);
+            cell_coord(H, __ldg(p.xs + j), __ldg(p.ys + i), p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy, p.kx, p.ky);
             t = make_tap(ix, iy, p.Wf, p.Hf, p.fsy16, p.fsx16);
         }
         const bool seen = t.flags != 0;
