@@ -617,3 +617,29 @@ def test_emulate_kornia_matches_from_spec_restatement(fusion):
                           warp_impl="kornia").to(DEV)(feats.to(DEV), K[None].to(DEV), Rt[None].to(DEV),
                                                        img_size=rig.WILDTRACK_IMG_SIZE).cpu().reshape(want.shape)
     assert float((ref - want).abs().median()) > 10 * float(diff.median()) + 1e-6
+
+
+# ---- no stray reads: the features live inside a NaN-filled allocation -------------------------------------------------
+
+@pytest.mark.parametrize("C,dtype", [(256, torch.float32), (136, torch.float32), (512, torch.bfloat16), (264, torch.bfloat16)])
+@pytest.mark.parametrize("mode", ["mean", "max", "none"])
+def test_features_inside_a_nan_halo(C, dtype, mode):
+    """The logical feature tensor is a window of a larger allocation filled with NaN (one texel of halo on every side
+    of every map, one 16-byte vector of halo on both sides of the channels).  Every tap the kernels blend -- also the
+    weight-0 stand-ins of out-of-map taps and the spare lanes of a partial chunk -- multiplies what it read, so a single
+    read outside the window would put a NaN into the output."""
+    from bevipm import _lib, ops
+    B, V, fhw, bhw = 2, 5, (31, 53), (37, 91)
+    feats, K, Rt, xs, ys, img = _rig_case(B, V, C, fhw, bhw, seed=43)
+    ve = 4 if dtype == torch.float32 else 8
+    f = torch.from_numpy(feats).to(dtype)
+    big = torch.full((B, V, fhw[0] + 2, fhw[1] + 2, C + 2 * ve), float("nan"), dtype=dtype, device=DEV)
+    win = big[:, :, 1:-1, 1:-1, ve:ve + C]
+    win.copy_(f.permute(0, 1, 3, 4, 2).to(DEV))
+    fv = win.permute(0, 1, 4, 2, 3)   # logical [B,V,C,Hf,Wf], channel stride 1, the other strides those of the big tensor
+    _, Kd, Rd, xd, yd = _dev_inputs(feats[:, :, :1], K, Rt, xs, ys, True)
+    out = ops.warp_fuse(fv, Kd, Rd, xd, yd, int(img[0]), int(img[1]), _lib.MODES[mode], False, 0)
+    torch.cuda.synchronize()
+    assert 30 <= int(_lib.load().bevipm_last_variant()) <= 39   # the run kernel took it (fast path on a strided window)
+    want = orc.warp_fuse(f.float().numpy(), K, Rt, xs, ys, img, mode)
+    assert _same(out.cpu().numpy(), want)
