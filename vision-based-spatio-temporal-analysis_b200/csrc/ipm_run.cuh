@@ -230,7 +230,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     const uint32_t s_wts = (uint32_t)__cvta_generic_to_shared(seg_wts(r));
     const uint32_t s_loads = (uint32_t)__cvta_generic_to_shared(seg_loads(r));
     const uint32_t s_meta = (uint32_t)__cvta_generic_to_shared(seg_meta(r));
-    // DEPTH > 0: this lane's 16 bytes of stage 0 / tap 0 in the warp's ring (stage = 2 KB, tap = 512 B)
+    // this lane's 16 bytes of stage 0 / tap 0 in the warp's ring (stage = 2 KB, tap = 512 B)
     uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + run_tables_bytes(V, CELLS, R) + warp * (DEPTH * 2048) + lane * 16;
     asm volatile("" : "+r"(ring));  // opaque: one register, not re-derived from %tid at every reload
     // TMA: one mbarrier per stage of this warp's ring, behind the homography table; entries issued / consumed so far
