@@ -205,7 +205,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     constexpr int ILP = (KMODE == KM_NONE) ? P : ((MAXREG <= 128 && P > 2 && CELLS >= 8) ? 2 : P);  // at 128 registers there is room for two chains in flight, not four
     static_assert(CELLS >= 2 && CELLS <= 16, "cells per segment");
     static_assert(NW % KSPLIT == 0 && (KSPLIT == 1 || KSPLIT == 2 || KSPLIT == 4), "warps per row segment");
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_run[];  // (its own symbol: the other kernels declare theirs 16-byte aligned)
 
     const int V = p.V;
     const int seg_bytes = run_seg_bytes(V, CELLS);
@@ -215,9 +215,9 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     const int i0 = ty * R, j0 = tx * CELLS;
     const int b0 = blockIdx.z * fpc, b1 = min(p.B, b0 + fpc);
 
-    auto seg_wts = [&](int r) { return reinterpret_cast<float4*>(smem_raw + r * seg_bytes); };
-    auto seg_loads = [&](int r) { return reinterpret_cast<int4*>(smem_raw + r * seg_bytes + V * CELLS * 16); };
-    auto seg_meta = [&](int r) { return reinterpret_cast<int*>(smem_raw + r * seg_bytes + V * CELLS * 16 + (V * CELLS + 8) * 16); };
+    auto seg_wts = [&](int r) { return reinterpret_cast<float4*>(smem_run + r * seg_bytes); };
+    auto seg_loads = [&](int r) { return reinterpret_cast<int4*>(smem_run + r * seg_bytes + V * CELLS * 16); };
+    auto seg_meta = [&](int r) { return reinterpret_cast<int*>(smem_run + r * seg_bytes + V * CELLS * 16 + (V * CELLS + 8) * 16); };
     // meta: [0, V) per-view mask (seen | reload << 16), [V, 2V) the views that see the segment, [2V] their
     // number, [2V+1] entries of the load list, [2V+2] mask of the cells EVERY view sees (max fusion)
 
@@ -231,10 +231,10 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     const uint32_t s_loads = (uint32_t)__cvta_generic_to_shared(seg_loads(r));
     const uint32_t s_meta = (uint32_t)__cvta_generic_to_shared(seg_meta(r));
     // this lane's 16 bytes of stage 0 / tap 0 in the warp's ring (stage = 2 KB, tap = 512 B)
-    uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_raw) + run_tables_bytes(V, CELLS, R) + warp * (DEPTH * 2048) + lane * 16;
+    uint32_t ring = (uint32_t)__cvta_generic_to_shared(smem_run) + run_tables_bytes(V, CELLS, R) + warp * (DEPTH * 2048) + lane * 16;
     asm volatile("" : "+r"(ring));  // opaque: one register, not re-derived from %tid at every reload
     // TMA: one mbarrier per stage of this warp's ring, behind the homography table; entries issued / consumed so far
-    uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_raw) + run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048) + V * 48 + warp * (DEPTH * 8);
+    uint32_t bars = (uint32_t)__cvta_generic_to_shared(smem_run) + run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048) + V * 48 + warp * (DEPTH * 8);
     uint32_t n_issue = 0, n_cons = 0;
     if constexpr (TMA) {
         if (lane == 0) {
@@ -251,7 +251,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     for (int b = b0; b < b1;) {
         if (b > b0) __syncthreads();  // every warp is done with the previous run's tables
         // ---- the V homographies of this frame, once per CTA (geometry.py:60-63): rows padded to 4 floats ------------
-        float* sH = reinterpret_cast<float*>(smem_raw + run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048));
+        float* sH = reinterpret_cast<float*>(smem_run + run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048));
         if (tid < V) {
             float H[9];
             homography(p.K + 9 * (b * V + tid), p.Rt + 12 * (b * V + tid), H);

@@ -16,7 +16,7 @@ namespace bevipm {
 template <typename TG, int CELLS, int NW>
 __global__ void __launch_bounds__(NW * 32) warp_fuse_run_bwd_kernel(const FwdParams p) {
     constexpr int R = NW;  // one warp per row segment
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_run[];  // (its own symbol: the other kernels declare theirs 16-byte aligned)
     const int V = p.V;
     const int seg_bytes = run_seg_bytes(V, CELLS);
     const int tid = threadIdx.x, lane = tid & 31;
@@ -24,10 +24,10 @@ __global__ void __launch_bounds__(NW * 32) warp_fuse_run_bwd_kernel(const FwdPar
     const int b = blockIdx.z;
     const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
     const int i = ty * R + warp, j0 = tx * CELLS;
-    float4* wts = reinterpret_cast<float4*>(smem_raw + warp * seg_bytes);
-    int4* loads = reinterpret_cast<int4*>(smem_raw + warp * seg_bytes + V * CELLS * 16);
-    int* ml = reinterpret_cast<int*>(smem_raw + warp * seg_bytes + V * CELLS * 16 + (V * CELLS + 8) * 16);
-    float* sH = reinterpret_cast<float*>(smem_raw + run_tables_bytes(V, CELLS, R));
+    float4* wts = reinterpret_cast<float4*>(smem_run + warp * seg_bytes);
+    int4* loads = reinterpret_cast<int4*>(smem_run + warp * seg_bytes + V * CELLS * 16);
+    int* ml = reinterpret_cast<int*>(smem_run + warp * seg_bytes + V * CELLS * 16 + (V * CELLS + 8) * 16);
+    float* sH = reinterpret_cast<float*>(smem_run + run_tables_bytes(V, CELLS, R));
 
     if (tid < V) {
         float H[9];
@@ -89,6 +89,8 @@ __global__ void __launch_bounds__(NW * 32) warp_fuse_run_bwd_kernel(const FwdPar
                 }
             }
             float2 ga[4][2];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) ga[t][0] = ga[t][1] = make_float2(0.0f, 0.0f);
             int4 o = make_int4(-1, -1, -1, -1);
             auto flush = [&]() {  // the block's four taps: one 16-byte atomic each (out-of-map taps carry -1)
                 if (o.x >= 0) atomicAdd(gbase + o.x, make_float4(ga[0][0].x, ga[0][0].y, ga[0][1].x, ga[0][1].y));
