@@ -140,7 +140,7 @@ bool run_kernel_ok(const FwdParams& p) {
     return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
 }
 
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = bevipm::KM_ACC, bool TMA = false>
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = bevipm::KM_ACC, bool TMA = false, bool HALF = false>
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = bevipm::VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
@@ -152,7 +152,7 @@ int launch_run(FwdParams p, cudaStream_t st) {
     p.fsy16 = (int)(p.fs_y / VE);
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
-    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE, TMA>;
+    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE, TMA, HALF>;
     const size_t smem = (size_t)bevipm::run_tables_bytes(p.V, CELLS, R) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8;  // tables, rings, homographies, ring barriers
     if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
@@ -238,11 +238,11 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
         // run kernel <cells per segment, warps per CTA, warps per segment, register cap, ring depth, .ca>:
         // 32 = fp32 default, 33 = bf16 default; the others are the sweep points quoted in profiles/r01_notes.md
-        case 30: return launch_run<TIn, TOut, 4, 4, 1, 96, 4, false>(p, st);
+        case 30: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_ACC, false, true>(p, st);   // half reloads
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
         case 32: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);
         case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
-        case 34: return launch_run<TIn, TOut, 8, 4, 1, 128, 5, false>(p, st);
+        case 34: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, bevipm::KM_ACC, false, true>(p, st);  // half reloads
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
         case 36: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_ACC, true>(p, st);    // TMA ring
         case 37: return launch_run<TIn, TOut, 16, 4, 1, 128, 4, false>(p, st);

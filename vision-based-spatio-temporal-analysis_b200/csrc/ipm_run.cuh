@@ -42,7 +42,7 @@ __host__ __device__ constexpr int run_tables_bytes(int V, int cells, int R);
 __host__ __device__ constexpr int run_seg_bytes(int V, int cells) {
     return V * cells * 16                    // blend weights (nw, ne, sw, se) of every (view, cell)
            + (V * cells + 8) * 16            // the load list (+8: entries the walk reads ahead but never copies)
-           + ((V * 8 + 12 + 15) / 16) * 16;  // per-view masks, compact view list, two totals, cells every view sees
+           + ((V * 12 + 12 + 15) / 16) * 16;  // per-view masks, view list, totals, cells every view sees, half-reload masks
 }
 
 __host__ __device__ constexpr int run_tables_bytes(int V, int cells, int R) { return (R * run_seg_bytes(V, cells) + 127) / 128 * 128; }
@@ -92,11 +92,25 @@ __device__ __forceinline__ void run_copy4(uint32_t stage, unsigned long long bas
     cp_async16<CA>(stage + 1536, tap_ptr(base, o.w));
 }
 
+// a load-list entry -> one ring stage: four taps, or (HALF entries: z = -2) the two taps of the new column
+template <bool CA, bool HALF>
+__device__ __forceinline__ void run_copy_entry(uint32_t stage, unsigned long long base, const int4& o) {
+    if (HALF && o.z < -1) {
+        cp_async16<CA>(stage, tap_ptr(base, o.x));
+        cp_async16<CA>(stage + 512, tap_ptr(base, o.y));
+    } else {
+        run_copy4<CA>(stage, base, o);
+    }
+}
+
 // ---- phase A of the run kernels: one warp builds one row segment's tables, directly in walking order -------------
 // lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view that sees
 // the segment its place in the view list (lane order = views ascending, cells ascending).  sH: the V homographies,
 // rows padded to 4 floats.  MARK_INVALID (backward): out-of-map taps carry offset -1 instead of a stand-in address.
-template <int CELLS, bool WANT_ALL_SEEN, bool MARK_INVALID>
+// HALF: a reload whose block is the previous one shifted by exactly one texel in x (both blocks fully inside the map)
+// becomes a HALF entry: only the new column's two taps are listed ({top, bottom, -2, 0}), the walk keeps the other
+// column in registers; per view, ml[2V+3+v] = half bits | (moved-to-the-east bits << 16).
+template <int CELLS, bool WANT_ALL_SEEN, bool MARK_INVALID, bool HALF = false>
 __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int i, int j0, int lane, int fsv16, const float* sH,
                                                  float4* wts, int4* loads, int* ml) {
     constexpr int GPW = 32 / CELLS;
@@ -126,6 +140,16 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
         const bool same = c > 0 && prev_seen && px0 == t.x0 && py0 == t.y0;
         const bool reload = seen && !same;  // the row enters a new 2x2 block here
         const unsigned reload_b = __ballot_sync(0xffffffffu, reload);
+        bool half = false, east = false;
+        unsigned half_b = 0, east_b = 0;
+        if constexpr (HALF) {
+            const int pfl = __shfl_up_sync(0xffffffffu, t.flags, 1);
+            const int dxs = t.x0 - px0;
+            half = reload && c > 0 && prev_seen && py0 == t.y0 && (dxs == 1 || dxs == -1) && t.flags == kTapMask && pfl == kTapMask;
+            east = half && dxs == 1;
+            half_b = __ballot_sync(0xffffffffu, half);
+            east_b = __ballot_sync(0xffffffffu, east);
+        }
         const int shift = gl * CELLS;
         const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
         const bool lead_seen = active && c == 0 && seen_c != 0;
@@ -148,8 +172,15 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
                 ww[tap] = nf ? qnan : (ok ? w[tap] : 0.0f);
             }
             wts[v * CELLS + c] = make_float4(ww[0], ww[1], ww[2], ww[3]);
-            if (reload) loads[nloads + __popc(reload_b & lt)] = make_int4(off[0], off[1], off[2], off[3]);
-            if (c == 0) ml[v] = (int)(seen_c | (reload_c << 16));
+            if (reload) {
+                int4 entry = make_int4(off[0], off[1], off[2], off[3]);
+                if (HALF && half) entry = east ? make_int4(off[1], off[3], -2, 0) : make_int4(off[0], off[2], -2, 0);  // the new column
+                loads[nloads + __popc(reload_b & lt)] = entry;
+            }
+            if (c == 0) {
+                ml[v] = (int)(seen_c | (reload_c << 16));
+                if (HALF) ml[2 * V + 3 + v] = (int)(((half_b >> shift) & CMASK) | (((east_b >> shift) & CMASK) << 16));
+            }
             if (lead_seen) ml[V + nseen + __popc(lead_b & lt)] = v;
         }
         nloads += __popc(reload_b);
@@ -194,10 +225,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views, zeros of views that miss a cell included (fusion.py:22),
 // KM_NONE = the per-view maps GeometryTransformer returns (geometry.py:162-163; what ConcatFusion reshapes): every (view, cell)
 // result is stored as soon as it is blended, zeros where a view does not see a cell; no accumulators at all.
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC, bool TMA = false>
+template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC, bool TMA = false,
+          bool HALF = false>
 __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
     static_assert(DEPTH >= 2 && DEPTH <= 8, "ring depth");
     static_assert(!TMA || (DEPTH & (DEPTH - 1)) == 0, "the TMA ring indexes its stages with a mask");
+    static_assert(!HALF || (!TMA && PROBE == 0), "half reloads are built for the cp.async ring only");
     using VT = VecTraits<TIn>;
     constexpr int VE = VT::VE, P = VT::P;
     constexpr int R = NW / KSPLIT;  // row segments per CTA
@@ -264,7 +297,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
         // lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view
         // that sees the segment its place in the view list (lane order = views ascending, cells ascending).
         if (kk == 0)
-            run_build_tables<CELLS, KMODE == KM_MAX, false>(p, V, i, j0, lane, fsv16, sH, seg_wts(r), seg_loads(r), seg_meta(r));
+            run_build_tables<CELLS, KMODE == KM_MAX, false, HALF>(p, V, i, j0, lane, fsv16, sH, seg_wts(r), seg_loads(r), seg_meta(r));
         if (KSPLIT > 1) __syncthreads();
         else __syncwarp();
 
@@ -330,7 +363,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 if constexpr (TMA) {
                     if (PROBE != 1 && o.x >= 0) issue_tma(base, o);
                 } else {
-                    if (PROBE != 1 && o.x >= 0) run_copy4<CA>(ring + s * 2048, base, o);
+                    if (PROBE != 1 && o.x >= 0) run_copy_entry<CA, HALF>(ring + s * 2048, base, o);
                     cp_async_commit();
                 }
             }
@@ -361,6 +394,8 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                     const int v = lds4i(s_meta + 4 * (V + vi));
                     const unsigned m = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_meta + 4 * v), 0);  // warp-uniform
                     const uint32_t wv = s_wts + v * (CELLS * 16);
+                    unsigned m2 = 0;  // HALF: which reloads only bring a new column, and on which side
+                    if constexpr (HALF) m2 = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_meta + 4 * (2 * V + 3 + v)), 0);
                     float4 wn = lds16f(wv);
                     // A cell the view does not see is never a reload; its blend runs on whatever `cur` holds
                     // and is simply not added (predicated), so the only branch per cell is "reload?".
@@ -387,6 +422,27 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                                 // the entry DEPTH-1 ahead goes into the stage unpacked at the previous reload
                                 if (PROBE != 1 && o.x >= 0) issue_tma(lbase, o);
                                 lp += 16;
+                            } else if (HALF && ((m2 >> c) & 1u)) {
+                            // the block moved by one texel in x: keep the shared column, unpack the new one
+                            cp_async_wait<DEPTH - 2>();
+                            const uint4 n0 = lds16(st_rd), n1 = lds16(st_rd + 512);
+                            const int4 o = lds16i(lp);
+                            if ((m2 >> (16 + c)) & 1u) {  // to the east: old NE / SE become NW / SW
+#pragma unroll
+                                for (int q = 0; q < P; ++q) { cur[0][q] = cur[1][q]; cur[2][q] = cur[3][q]; }
+                                VT::unpack(n0, cur[1]);
+                                VT::unpack(n1, cur[3]);
+                            } else {                       // to the west
+#pragma unroll
+                                for (int q = 0; q < P; ++q) { cur[1][q] = cur[0][q]; cur[3][q] = cur[2][q]; }
+                                VT::unpack(n0, cur[0]);
+                                VT::unpack(n1, cur[2]);
+                            }
+                            if (o.x >= 0) run_copy_entry<CA, HALF>(st_wr, lbase, o);
+                            cp_async_commit();
+                            lp += 16;
+                            st_wr = st_rd;
+                            st_rd = (st_rd == ring + (DEPTH - 1) * 2048) ? ring : st_rd + 2048;
                             } else {
                             cp_async_wait<DEPTH - 2>();  // the oldest entry has landed (a lane reads back its own bytes)
                             uint4 nxt[4];
@@ -396,7 +452,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
 #pragma unroll
                             for (int tap = 0; tap < 4; ++tap) VT::unpack(nxt[tap], cur[tap]);
                             // the entry DEPTH-1 ahead goes into the stage unpacked at the previous reload
-                            if (PROBE != 1 && o.x >= 0) run_copy4<CA>(st_wr, lbase, o);
+                            if (PROBE != 1 && o.x >= 0) run_copy_entry<CA, HALF>(st_wr, lbase, o);
                             cp_async_commit();
                             lp += 16;
                             st_wr = st_rd;
