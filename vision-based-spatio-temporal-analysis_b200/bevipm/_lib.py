@@ -93,4 +93,6 @@ def variant_name(v: int) -> str:
         return f"warp_fuse_list_kernel (variant {v})"
     if 30 <= v <= 41:
         return f"warp_fuse_run_kernel (variant {v})"
+    if 50 <= v <= 52:
+        return f"warp_fuse_staged_kernel (TMA-staged tiles, variant {v})"
     return f"variant {v}"
