@@ -128,12 +128,14 @@ def test_staged_view_counts(views):
                                      ((64, 96), (33, 70)),       # mixed: tile stages, row stages and boxes
                                      ((9, 12), (60, 150)),       # BEV far denser than a tiny source map
                                      ((200, 300), (24, 64))])
-@pytest.mark.parametrize("slot", [16384, 24576, 65536])
-def test_staged_every_stage_kind(monkeypatch, variant, fhw, bhw, slot):
-    """Footprints from far smaller to far larger than one ring slot: views are staged per tile, per BEV row or per
-    2x2 block (ipm_staged.cuh, phase A); the slot size moves the boundaries between the three."""
-    monkeypatch.setenv("BEVIPM_ST_S", str(slot))
-    monkeypatch.setenv("BEVIPM_ST_D", "3")
+@pytest.mark.parametrize("ring,cap,lag", [(32768, 16384, 1), (49152, 16384, 2), (65536, 32768, 3), (98304, 98304, 2)])
+def test_staged_every_stage_kind(monkeypatch, variant, fhw, bhw, ring, cap, lag):
+    """Footprints from far smaller to far larger than the largest stage: views are staged per tile, per group of BEV
+    rows, per row or per 2x2 block (ipm_staged.cuh, phase A); ring size, stage cap and arming lag move the
+    boundaries and the copy schedule."""
+    monkeypatch.setenv("BEVIPM_ST_RING", str(ring))
+    monkeypatch.setenv("BEVIPM_ST_CAP", str(cap))
+    monkeypatch.setenv("BEVIPM_ST_LAG", str(lag))
     feats, K, Rt, xs, ys, img = _rig_case(1, 7, 128, fhw, bhw, seed=sum(fhw) + sum(bhw))
     want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")
     out = _run(feats, K, Rt, xs, ys, img, "mean", True, variant=variant).cpu().numpy()

@@ -19,7 +19,7 @@ wl = rig.WORKLOADS[sys.argv[1]]
 specs = sys.argv[2].split(",")
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 iters = int(sys.argv[4]) if len(sys.argv) > 4 else 50
-SWITCHES = ("BEVIPM_ST_S", "BEVIPM_ST_D", "BEVIPM_RUN_FPC", "BEVIPM_ST_LOOK")
+SWITCHES = ("BEVIPM_ST_RING", "BEVIPM_ST_CAP", "BEVIPM_ST_LAG", "BEVIPM_ST_CPS", "BEVIPM_RUN_FPC")
 res = {s: [] for s in specs}
 for _ in range(reps):
     for s in specs:

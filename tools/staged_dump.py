@@ -17,106 +17,135 @@ for p in (str(ROOT), str(ROOT / "vision-based-spatio-temporal-analysis_b200"), s
     sys.path.insert(0, p)
 import numpy as np
 
-CELLS, ROWS_T, ROWS_R = 8, 32, 12
+CELLS, ROWS_G, ROWS_R = 8, 32, 12
 WIDTHS = [2, 4, 6, 8, 10, 12, 14, 16, 20, 24, 32, 48, 64]
 
 
-def layout(V, R, S, D):
+def layout(V, R):
     up = lambda x, a: (x + a - 1) // a * a
     L, o = {}, 0
+    L["nst_max"] = V * R
+    L["gt"] = max(ROWS_G, R * 16)
+    L["max_ops"] = V * L["gt"]
     L["wts"] = o; o += R * V * CELLS * 16
     L["ent"] = o; o += R * V * CELLS * 8
-    L["mask"] = o; o += up(R * V * 4, 16)
-    L["stg"] = o; o += V * R * 16
-    max_ops = V * max(ROWS_T, R * ROWS_R)
-    L["ops"] = o; o += max_ops * 8
+    L["wst"] = o; o += up(R * L["nst_max"] * 4, 16)
+    L["sdesc"] = o; o += L["nst_max"] * 16
+    L["ops"] = o; o += L["max_ops"] * 8
+    L["bars"] = o; o += up(2 * L["nst_max"] * 8, 16)
     L["misc"] = o; o += 128
     L["sH"] = o; o += V * 48
-    L["bars"] = o; o += up(2 * D * 8, 128)
     L["ring"] = up(o, 128)
     return L
 
 
 def check(path, x0, y0, Hf, Wf, verbose=False):
     raw = open(path, "rb").read()
-    V, NW, S, D, ring, gx, gz, tiles_x, tiles_y, fpc, Hb, Wb, Hf2, Wf2, C, es = struct.unpack("16i", raw[:64])
-    L = layout(V, NW, S, D)
+    V, NW, ring_bytes, cap, ring, gx, gz, tiles_x, tiles_y, fpc, Hb, Wb, Hf2, Wf2, C, es = struct.unpack("16i", raw[:64])
+    L = layout(V, NW)
     assert L["ring"] == ring, (L["ring"], ring)
     body = np.frombuffer(raw[64:], np.uint8).reshape(gz, gx, ring)
     errs = 0
-    kinds = {"tile": 0, "rows": 0, "blocks": 0}
+    kinds = {"multi-row": 0, "one-row": 0, "blocks": 0}
     staged_texels = 0
+    nst_hist = []
     for cta in range(gx):
         sm = body[0, cta]
         ty, tx = divmod(cta, tiles_x)
         i0, j0 = ty * NW, tx * CELLS
         i32 = lambda off, n: sm[off:off + 4 * n].view(np.int32)
         nst = int(i32(L["misc"], 1)[0])
-        stg = i32(L["stg"], 4 * V * NW).reshape(-1, 4)[:nst]
-        ops = i32(L["ops"], 2 * V * max(ROWS_T, NW * ROWS_R)).reshape(-1, 2)
-        mask = sm[L["mask"]:L["mask"] + 4 * NW * V].view(np.uint32).reshape(NW, V)
+        nst_hist.append(nst)
+        sdesc = i32(L["sdesc"], 4 * L["nst_max"]).reshape(-1, 4)[:nst]
+        ops = i32(L["ops"], 2 * L["max_ops"]).reshape(-1, 2)
+        wst = sm[L["wst"]:L["wst"] + 4 * NW * L["nst_max"]].view(np.uint32).reshape(NW, L["nst_max"])
         ent = i32(L["ent"], 2 * NW * V * CELLS).reshape(NW, V, CELLS, 2)
         stage_of = {}
-        texmaps = []
+        texmaps, regions = [], []
         last_v = -1
-        for s, (v, rowmask, nbytes, opw) in enumerate(stg):
+        for s, (nbytes, yw, opw, vw) in enumerate(sdesc):
+            v, rowmask = vw & 0xff, (vw >> 8) & 0xffff
+            off, dback = (yw & 0xffff) << 7, yw >> 16
+            regions.append((off, nbytes, dback))
             o0, n = opw & 0xffff, opw >> 16
             if v < last_v:
                 print(f"cta {cta}: stage {s} view {v} after view {last_v}"); errs += 1
             last_v = v
+            if nbytes > cap or off + nbytes > ring_bytes:
+                print(f"cta {cta} stage {s}: {nbytes} bytes at {off} (cap {cap}, ring {ring_bytes})"); errs += 1
             tm = {}
             tot = 0
+            isblk = False
             for q in range(n):
-                a, b = int(ops[o0 + q, 0]), int(ops[o0 + q, 1])
+                a, bb = int(ops[o0 + q, 0]), int(ops[o0 + q, 1])
                 x = ((a & 0xffff) ^ 0x8000) - 0x8000
                 y = a >> 16
-                off = (b & 0xffff) * 16
-                mp = b >> 16
+                o16 = (bb & 0xffff) * 16
+                mp = bb >> 16
                 if mp == 13:
                     w, h = 2, 2
-                    kinds["blocks"] += 1
+                    isblk = True
                 else:
                     w, h = WIDTHS[mp], 1
                 tot += w * h * 512
                 for yy in range(h):
                     for xx in range(w):
-                        o = off + (yy * w + xx) * 512
-                        if o in tm or o + 512 > S:
-                            print(f"cta {cta} stage {s}: copy {q} overlaps / leaves the slot at {o}"); errs += 1
+                        o = o16 + (yy * w + xx) * 512
+                        if o in tm or o + 512 > max(nbytes, 0):
+                            print(f"cta {cta} stage {s}: copy {q} overlaps / leaves the stage at {o}"); errs += 1
                         tm[o] = (x + xx, y + yy)
             if tot != nbytes:
                 print(f"cta {cta} stage {s}: barrier expects {nbytes} bytes, copies deliver {tot}"); errs += 1
             staged_texels += tot // 512
-            if bin(rowmask).count("1") > 1 or NW == 1:
-                kinds["tile"] += 1
-            else:
-                kinds["rows"] += 1
+            kinds["blocks" if isblk else ("multi-row" if bin(rowmask).count("1") > 1 else "one-row")] += 1
             texmaps.append(tm)
             for r in range(NW):
                 if (rowmask >> r) & 1:
                     if (r, v) in stage_of:
                         print(f"cta {cta}: (row {r}, view {v}) in two stages"); errs += 1
                     stage_of[(r, v)] = s
+        # ring places: nothing among the dback-1 stages before s (cyclically) may overlap s; stage s-dback does (or dback == nst)
+        for s, (off, nb, dback) in enumerate(regions):
+            if nb == 0:
+                continue
+            for k in range(1, nst + 1):
+                q = (s - k) % nst
+                qo, qb, _ = regions[q]
+                hit = (qb > 0 and qo < off + nb and off < qo + qb) or k == nst
+                if hit:
+                    if k != dback:
+                        print(f"cta {cta} stage {s}: first overlap {k} stages back, table says {dback}"); errs += 1
+                    break
         for r in range(NW):
             i = i0 + r
             for v in range(V):
-                seen_want = 0
+                seen_want, rl_want = 0, 0
+                prev = None
                 for c in range(CELLS):
                     j = j0 + c
                     if i < Hb and j < Wb and -1 <= x0[v, i, j] <= Wf - 1 and -1 <= y0[v, i, j] <= Hf - 1:
                         seen_want |= 1 << c
-                seen = int(mask[r, v]) & 0xffff
-                if seen != seen_want:
-                    print(f"cta {cta} row {r} view {v}: seen mask {seen:08b} want {seen_want:08b}"); errs += 1
+                        cur = (int(x0[v, i, j]), int(y0[v, i, j]))
+                        if cur != prev:
+                            rl_want |= 1 << c
+                        prev = cur
+                    else:
+                        prev = None
+                words = [(s, int(wst[r, s])) for s in range(nst) if int(wst[r, s]) and (int(wst[r, s]) >> 24) == v]
+                if not seen_want:
+                    if words:
+                        print(f"cta {cta} row {r} view {v}: stage words {words} but nothing seen"); errs += 1
                     continue
-                if seen and (r, v) not in stage_of:
-                    print(f"cta {cta} row {r} view {v}: seen {seen:08b} but no stage"); errs += 1
+                if len(words) != 1 or (r, v) not in stage_of or words[0][0] != stage_of[(r, v)]:
+                    print(f"cta {cta} row {r} view {v}: stage words {words}, stage list says {stage_of.get((r, v))}"); errs += 1
                     continue
-                if not seen:
+                w = words[0][1]
+                if (w & 0xff) != seen_want or ((w >> 8) & 0xff) != rl_want:
+                    print(f"cta {cta} row {r} view {v}: seen/reload {w & 0xff:08b}/{(w >> 8) & 0xff:08b} want {seen_want:08b}/{rl_want:08b}"); errs += 1
                     continue
                 tm = texmaps[stage_of[(r, v)]]
                 for c in range(CELLS):
-                    if not (seen >> c) & 1:
+                    if not (seen_want >> c) & 1:
                         continue
                     X, Y = int(x0[v, i0 + r, j0 + c]), int(y0[v, i0 + r, j0 + c])
                     top, bot = int(ent[r, v, c, 0]), int(ent[r, v, c, 1])
@@ -126,7 +155,8 @@ def check(path, x0, y0, Hf, Wf, verbose=False):
                         print(f"cta {cta} (tile {ty},{tx}) row {r} view {v} cell {c}: taps {got} want {want} (ent {top},{bot}, stage {stage_of[(r, v)]})")
                         errs += 1
         if verbose:
-            print(f"cta {cta}: {nst} stages", [tuple(int(z) for z in s) for s in stg])
+            print(f"cta {cta}: {nst} stages", [tuple(int(z) for z in s) for s in sdesc])
+    print(f"stages per tile: mean {np.mean(nst_hist):.2f} max {max(nst_hist)}; ring {ring_bytes} cap {cap}")
     return errs, kinds, staged_texels
 
 

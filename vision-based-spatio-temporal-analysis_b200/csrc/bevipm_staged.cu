@@ -83,19 +83,29 @@ int env_int(const char* name, int dflt) {
 }
 
 template <typename TIn, typename TOut, int NW, int KMODE, int PROBE>
-int launch_t(FwdParams p, int S, int D, int ctas_per_sm, cudaStream_t st, char* err, size_t errlen) {
+int launch_t(FwdParams p, int ctas_per_sm, cudaStream_t st, char* err, size_t errlen) {
     constexpr int VE = VecTraits<TIn>::VE;
     p.tiles_x = (p.Wb + kStCells - 1) / kStCells;
     p.tiles_y = (p.Hb + NW - 1) / NW;
     p.fsy16 = (int)(p.fs_y / VE);
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
-    const StagedSmem L(p.V, NW, S, D);
-    if (L.total > 227 * 1024 || L.scratch_end > L.total)
-        return st_fail(err, errlen, BEVIPM_ERR_UNSUPPORTED, "staged kernel: V=%d needs %d bytes of shared memory (tables + %d x %d ring)", p.V,
-                       std::max(L.total, L.scratch_end), D, S);
+    // shared memory: the tables, then the stage ring with whatever is left of this CTA's share of the SM (the driver
+    // keeps 1 KB per resident CTA); the ring must hold phase A's scratch arrays and two stages of the largest kind
+    const StagedSmem L(p.V, NW);
+    int ring = ((227 * 1024 - ctas_per_sm * 1024) / ctas_per_sm - L.ring) & ~511;
+    ring = env_int("BEVIPM_ST_RING", ring);
+    const int scratch = L.scratch_end - L.ring;
+    if (ring < scratch) ring = (scratch + 511) & ~511;
+    if (ring < 32 * 1024) ring = 32 * 1024;                  // many views: fewer CTAs per SM rather than no kernel
+    if (L.ring + ring > 227 * 1024)
+        return st_fail(err, errlen, BEVIPM_ERR_UNSUPPORTED, "staged kernel: V=%d needs %d bytes of shared memory", p.V, L.ring + ring);
+    int cap = env_int("BEVIPM_ST_CAP", ring / 2);            // largest stage: half the ring, so that the next one can fly
+    cap = std::max(16 * 1024, std::min(cap, ring)) & ~511;   // (a BEV row staged block by block takes up to 8 x 2 KB)
+    const int lag = std::max(1, std::min(env_int("BEVIPM_ST_LAG", 2), 8));
+    const int smem = L.ring + ring;
     auto kern = warp_fuse_staged_kernel<TIn, TOut, NW, 128, KMODE, PROBE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return st_fail(err, errlen, BEVIPM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
     // frames per CTA: phase A is shared by consecutive frames with the same calibration; keep >= 8 CTA waves
     int fpc = 1;
@@ -104,7 +114,6 @@ int launch_t(FwdParams p, int S, int D, int ctas_per_sm, cudaStream_t st, char* 
         while (fpc < 8 && fpc * 2 <= p.B && tiles * ((p.B + fpc * 2 - 1) / (fpc * 2)) >= 8 * slots) fpc *= 2;
         fpc = std::max(1, std::min(env_int("BEVIPM_RUN_FPC", fpc), p.B));
     }
-    const int look = std::max(1, std::min(env_int("BEVIPM_ST_LOOK", D - 2), D - 1));  // stages armed ahead of the one being walked
     dim3 grid(p.tiles_x * p.tiles_y, 1, (p.B + fpc - 1) / fpc);
     if (const char* path = getenv("BEVIPM_ST_DUMP")) {
         // development aid: phase A only, the shared-memory tables of every tile go to a file (tools/staged_dump.py reads it)
@@ -112,13 +121,13 @@ int launch_t(FwdParams p, int S, int D, int ctas_per_sm, cudaStream_t st, char* 
         unsigned char* d = nullptr;
         if (cudaMalloc(&d, n) != cudaSuccess) return st_fail(err, errlen, BEVIPM_ERR_CUDA, "dump buffer");
         cudaMemsetAsync(d, 0, n, st);
-        kern<<<grid, NW * 32, L.total, st>>>(p, fpc, S, D, look, g_maps, d);
+        kern<<<grid, NW * 32, smem, st>>>(p, fpc, ring, cap, lag, g_maps, d);
         cudaStreamSynchronize(st);
         unsigned char* h = (unsigned char*)malloc(n);
         cudaMemcpy(h, d, n, cudaMemcpyDeviceToHost);
         cudaFree(d);
         if (FILE* f = fopen(path, "wb")) {
-            const int hdr[16] = {p.V, NW, S, D, L.ring, (int)grid.x, (int)grid.z, p.tiles_x, p.tiles_y, fpc, p.Hb, p.Wb, p.Hf, p.Wf, p.C, (int)sizeof(TIn)};
+            const int hdr[16] = {p.V, NW, ring, cap, L.ring, (int)grid.x, (int)grid.z, p.tiles_x, p.tiles_y, fpc, p.Hb, p.Wb, p.Hf, p.Wf, p.C, (int)sizeof(TIn)};
             fwrite(hdr, sizeof(hdr), 1, f);
             fwrite(h, 1, n, f);
             fclose(f);
@@ -128,17 +137,17 @@ int launch_t(FwdParams p, int S, int D, int ctas_per_sm, cudaStream_t st, char* 
         if (e != cudaSuccess) return st_fail(err, errlen, BEVIPM_ERR_CUDA, "staged kernel (dump): %s", cudaGetErrorString(e));
         return 0;
     }
-    kern<<<grid, NW * 32, L.total, st>>>(p, fpc, S, D, look, g_maps, nullptr);
+    kern<<<grid, NW * 32, smem, st>>>(p, fpc, ring, cap, lag, g_maps, nullptr);
     e = cudaGetLastError();
     if (e != cudaSuccess) return st_fail(err, errlen, BEVIPM_ERR_CUDA, "staged kernel launch: %s", cudaGetErrorString(e));
     return 0;
 }
 
 template <typename TIn, typename TOut, int NW>
-int launch_mode(const FwdParams& p, int S, int D, int cps, int probe, cudaStream_t st, char* err, size_t errlen) {
-    if (p.mode == BEVIPM_MAX) return launch_t<TIn, TOut, NW, KM_MAX, 0>(p, S, D, cps, st, err, errlen);
-    if (probe == 1) return launch_t<TIn, TOut, NW, KM_ACC, 1>(p, S, D, cps, st, err, errlen);
-    return launch_t<TIn, TOut, NW, KM_ACC, 0>(p, S, D, cps, st, err, errlen);
+int launch_mode(const FwdParams& p, int cps, int probe, cudaStream_t st, char* err, size_t errlen) {
+    if (p.mode == BEVIPM_MAX) return launch_t<TIn, TOut, NW, KM_MAX, 0>(p, cps, st, err, errlen);
+    if (probe == 1) return launch_t<TIn, TOut, NW, KM_ACC, 1>(p, cps, st, err, errlen);
+    return launch_t<TIn, TOut, NW, KM_ACC, 0>(p, cps, st, err, errlen);
 }
 
 }  // namespace
@@ -161,24 +170,11 @@ bool staged_supported(const FwdParams& p, bool in_bf16) {
 int launch_staged(FwdParams p, bool in_bf16, bool out_bf16, int shape, int probe, cudaStream_t st, char* err, size_t errlen) {
     if (!staged_supported(p, in_bf16)) return st_fail(err, errlen, BEVIPM_ERR_UNSUPPORTED, "staged kernel: strides / extents / mode not supported");
     if (int rc = build_maps(p, in_bf16, err, errlen)) return rc;
-    // ring: D slots of S bytes.  8-row tiles: 2 CTAs per SM (<= 112.5 KB each incl. the tables); 4-row tiles: 3 CTAs per SM.
-    // A slot must hold one BEV row staged block by block (8 blocks of 2 KB); beyond that the largest that fits.
-    const int nw = shape == 1 ? 4 : 8;
-    const int cps = shape == 1 ? 3 : 2;
-    int D = env_int("BEVIPM_ST_D", shape == 1 ? 3 : 4);
-    if (D < 3 || D > 16) return st_fail(err, errlen, BEVIPM_ERR_BAD_ARG, "staged kernel: %d ring slots (3..16)", D);
-    int S;
-    {
-        const int budget = (227 * 1024 - cps * 1024) / cps;
-        S = std::min(24 * 1024, ((budget - StagedSmem(p.V, nw, 16 * 1024, D).ring) / D) & ~511);
-        while (S < 16 * 1024 && D > 3) { --D; S = std::min(24 * 1024, ((budget - StagedSmem(p.V, nw, 16 * 1024, D).ring) / D) & ~511); }
-        S = std::max(S, 16 * 1024);   // many views: fewer CTAs per SM rather than no kernel
-    }
-    S = env_int("BEVIPM_ST_S", S);
-    if (S < 16 * 1024 || S > 64 * 1024 || (S & 511))
-        return st_fail(err, errlen, BEVIPM_ERR_BAD_ARG, "staged kernel: slot bytes %d (16K..64K, multiple of 512)", S);
+    // 8-row tiles: 2 CTAs per SM; 4-row tiles: 4 CTAs per SM
+    const int cps = env_int("BEVIPM_ST_CPS", shape == 1 ? 4 : 2);
+    if (cps < 1 || cps > 8) return st_fail(err, errlen, BEVIPM_ERR_BAD_ARG, "staged kernel: %d CTAs per SM", cps);
 #define BEVIPM_ST_GO(TI, TO)                                                                       \
-    return shape == 1 ? launch_mode<TI, TO, 4>(p, S, D, cps, probe, st, err, errlen) : launch_mode<TI, TO, 8>(p, S, D, cps, probe, st, err, errlen)
+    return shape == 1 ? launch_mode<TI, TO, 4>(p, cps, probe, st, err, errlen) : launch_mode<TI, TO, 8>(p, cps, probe, st, err, errlen)
     if (!in_bf16 && !out_bf16) BEVIPM_ST_GO(float, float);
     if (in_bf16 && out_bf16) BEVIPM_ST_GO(__nv_bfloat16, __nv_bfloat16);
     if (in_bf16 && !out_bf16) BEVIPM_ST_GO(__nv_bfloat16, float);

@@ -8,22 +8,28 @@
 // tile's taps fall into; all warps of the CTA then blend from shared memory with LDS.128:
 //
 //   phase A (once per tile and run of frames with equal calibration): every (row, view, cell) is projected once
-//            (cell_coord + make_tap); per view the taps' texel rows and, per texel row, the span of x they touch are
-//            collected with shared-memory atomics, for the whole tile and for every BEV row on its own.  A view whose
-//            tile-level spans fit one ring slot becomes ONE stage (a list of row copies: tensor-map boxes of
-//            [256 channels x BW texels x 1 row], BW quantised to the widths the launcher encoded maps for); otherwise
-//            every BEV row of the tile becomes its own stage, from its own spans or -- when even those do not fit (the
-//            BEV is coarser than the source map there) -- from one [256 x 2 x 2] box per 2x2 block the row enters.
-//            Out-of-map parts of a box are zero-filled by the TMA unit: exactly the reference's zero padding
-//            (grid_sample padding_mode='zeros': a tap outside the map contributes 0 * w), so there is no tap mask,
-//            no stand-in address and no special case for non-finite features.
-//   phase B: the stage list of the tile is walked once per (frame, channel chunk) item.  A ring of D slots of S bytes
-//            in shared memory holds the stages in flight; full[slot] (transaction bytes) / empty[slot] (one arrival
-//            per warp) mbarriers order TMA writes and LDS reads.  The warps take turns at issuing: warp n % NW arms
-//            stage n + LOOK (LOOK = D - 2: it waits for the slowest warp to leave stage n - 2, not n - 1) when it starts stage n.  A warp owns one BEV row segment of 8 cells, keeps the 8 cells'
-//            accumulators in registers and walks a stage like the run kernel walks a view: on a reload bit it reads
-//            the 2x2 block from the slot (4 x LDS.128), unpacks it once, and blends it for as many cells as stay in
-//            the block.  Per cell the views are still added in ascending order: the reference's accumulation order.
+//            (cell_coord + make_tap); per (BEV row, view) the taps' texel rows and, per texel row, the span of x they
+//            touch are collected with shared-memory atomics.  Per view the rows are then grouped: the whole tile if the
+//            merged spans fit `cap` bytes, else its halves, quarters, ... single BEV rows; a row whose own spans do
+//            not fit (the BEV is coarser than the source map there) is staged as one [2 x 2] box per 2x2 block it
+//            enters.  A group is one STAGE: a list of row copies, tensor-map boxes of [256 channels x BW texels x 1
+//            row], BW quantised to the widths the launcher encoded maps for.  Out-of-map parts of a box are
+//            zero-filled by the TMA unit: exactly the reference's zero padding (grid_sample padding_mode='zeros': a
+//            tap outside the map contributes 0 * w), so there is no tap mask, no stand-in address and no special
+//            case for non-finite features.
+//            The stages of one (frame, channel chunk) item get STATIC places in a ring of shared memory (sequential
+//            placement, wrapping to offset 0) and, each, the distance back to the last stage that used any of its
+//            bytes before: the whole copy schedule is periodic and known before the first copy is issued.
+//   phase B: the stage list is walked once per item.  Every stage has its own full (transaction bytes) / empty (one
+//            arrival per warp) mbarrier pair, phase parity = item parity.  The warps take turns at issuing: before
+//            stage g is walked, warp g % NW arms every stage whose predecessor in the ring was stage g - LAG or
+//            older (it waits for that predecessor's empty barrier first), so copies run as far ahead as the ring
+//            holds.  A warp owns one BEV row segment of 8 cells, keeps the 8 cells' accumulators in registers and
+//            walks a stage like the run kernel walks a view: on a reload bit it reads the 2x2 block from the stage's
+//            place (4 x LDS.128), unpacks it once, and blends it for as many cells as stay in the block.  Per cell
+//            the views are still added in ascending order: the reference's accumulation order.
+//            Every warp waits for and releases every stage, also those that hold nothing for its row: that keeps all
+//            warps within one ring revolution of each other, which is what makes parity waits unambiguous.
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -34,10 +40,10 @@
 
 namespace bevipm {
 
-constexpr int kStCells = 8;    // cells per row segment (one warp)
-constexpr int kStRowsT = 32;   // texel rows a tile-level stage may span
-constexpr int kStRowsR = 12;   // texel rows a row-level stage may span
-constexpr int kStNumW = 13;    // span widths with a tensor map of their own
+constexpr int kStCells = 8;      // cells per row segment (one warp)
+constexpr int kStRowsG = 32;     // texel rows a group stage may span
+constexpr int kStRowsR = 12;     // texel rows one BEV row's spans may cover (else the row is staged block by block)
+constexpr int kStNumW = 13;      // span widths with a tensor map of their own
 constexpr int kStBlockMap = 13;  // the [2 x 2] block map
 constexpr int kStNumMaps = 14;
 
@@ -61,33 +67,34 @@ struct alignas(64) StagedMaps {
 
 // shared-memory layout of one CTA: persistent tables, then the ring (phase A's scratch aliases the ring)
 struct StagedSmem {
-    int wts, ent, mask, stg, ops, misc, sH, bars, ring, total;
-    int xy, yt, yr, tsp, rsp, trow, rrow, vinfo, rinfo, scratch_end;
-    int max_ops;
-    __host__ __device__ StagedSmem(int V, int R, int S, int D) {
+    int wts, ent, wst, sdesc, ops, bars, misc, sH, ring;           // persistent
+    int xy, mask, yr, rsp, gtab, ginfo, vst, vcnt, soff, scratch_end;  // scratch, inside the ring
+    int nst_max, max_ops, gt;
+    __host__ __device__ StagedSmem(int V, int R) {
         auto up = [](int x, int a) { return (x + a - 1) / a * a; };
+        nst_max = V * R;                                 // a view is at most R stages (one per BEV row)
+        gt = kStRowsG > R * 16 ? kStRowsG : R * 16;      // planned texel rows per view: R/2 pairs x 32 rows at most
+        max_ops = V * gt;
         int o = 0;
         wts = o; o += R * V * kStCells * 16;             // float4 (nw, ne, sw, se) per (row, view, cell)
-        ent = o; o += R * V * kStCells * 8;              // int2 (byte offset of the NW tap, of the SW tap) inside the slot
-        mask = o; o += up(R * V * 4, 16);                // seen | reload << 16 per (row, view)
-        stg = o; o += V * R * 16;                        // int4 {view, row mask, bytes, first op | ops << 16}
-        max_ops = V * (kStRowsT > R * kStRowsR ? kStRowsT : R * kStRowsR);
-        ops = o; o += max_ops * 8;                       // int2 {x | y << 16, slot offset / 16 | map << 16}
+        ent = o; o += R * V * kStCells * 8;              // int2 (byte offset of the NW tap, of the SW tap) inside the stage
+        wst = o; o += up(R * nst_max * 4, 16);           // per (row, stage): seen | reload << 8 | view << 24; 0 = not this row's
+        sdesc = o; o += nst_max * 16;                    // int4 {bytes, ring offset / 128 | dback << 16, first op | ops << 16, view}
+        ops = o; o += max_ops * 8;                       // int2 {x | y << 16, stage offset / 16 | map << 16}
+        bars = o; o += up(2 * nst_max * 8, 16);          // full[nst_max], empty[nst_max]
         misc = o; o += 128;                              // [0] stages, [1 + r] cells of row r every view sees
         sH = o; o += V * 48;                             // homographies, rows padded to 4 floats
-        bars = o; o += up(2 * D * 8, 128);               // full[D], empty[D]
         ring = up(o, 128);
-        total = ring + D * S;
         o = ring;
         xy = o; o += R * V * kStCells * 4;               // x0 | y0 << 16
-        yt = o; o += up(2 * V * 4, 16);                  // tile-level min / max texel row per view
-        yr = o; o += up(2 * R * V * 4, 16);              // row-level
-        tsp = o; o += V * kStRowsT * 8;                  // tile-level x spans per (view, texel row): lo, hi
-        rsp = o; o += R * V * kStRowsR * 8;              // row-level
-        trow = o; o += V * kStRowsT * 4;                 // planned rows: slot offset in texels | map << 12 | x lo << 16
-        rrow = o; o += R * V * kStRowsR * 4;
-        vinfo = o; o += V * 32;                          // per view: kind, stages, ops, bytes, row mask
-        rinfo = o; o += R * V * 16;                      // per (row, view): kind, ops, bytes, real-reload mask
+        mask = o; o += up(R * V * 4, 16);                // seen | reload << 16 per (row, view)
+        yr = o; o += up(2 * R * V * 4, 16);              // min / max texel row per (row, view)
+        rsp = o; o += R * V * kStRowsR * 8;              // x spans per (row, view, texel row): lo, hi
+        gtab = o; o += V * gt * 4;                       // planned texel rows: stage offset in texels | map << 12 | x lo << 16
+        ginfo = o; o += R * V * 16;                      // per (row, view): kind, first gtab row of its group, group's first texel row, real reloads
+        vst = o; o += V * R * 32;                        // per (view, stage of the view): row mask, bytes, ops, kind, gtab row, first texel row, texel rows, row
+        vcnt = o; o += up(V * 8, 16);                    // per view: stages, ops
+        soff = o; o += nst_max * 4;                      // ring offsets while the places are dealt
         scratch_end = o;
     }
 };
@@ -110,35 +117,36 @@ __device__ __forceinline__ int2 lds8i(uint32_t addr) {
     return v;
 }
 
-enum { ST_NONE = 0, ST_TILE = 1, ST_ROWS = 2, ST_SPANS = 1, ST_BLOCKS = 2 };
+enum { ST_SPANS = 1, ST_BLOCKS = 2 };
 
 // ---- phase A ------------------------------------------------------------------------------------------------------
-// Builds, for the tile at (i0, j0) of frame b: blend weights, reload masks, the stage list with its row copies and
-// every (row, view, cell)'s tap offsets inside its stage.  Five block barriers; the scratch arrays live in the ring.
+// Builds, for the tile at (i0, j0) of frame b: blend weights, the stage list with its row copies, ring places and
+// predecessor distances, every (row, view, cell)'s tap offsets inside its stage and every warp's per-stage word.
 template <int NW, bool WANT_ALL_SEEN>
-__device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSmem& L, unsigned char* sm, int S, int i0, int j0, int b) {
+__device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSmem& L, unsigned char* sm, int ring_bytes, int cap, int i0, int j0, int b) {
     constexpr int CELLS = kStCells, GPW = 32 / CELLS, NT = NW * 32;
     constexpr unsigned CMASK = (1u << CELLS) - 1u;
-    const int V = p.V;
+    static_assert(NW == 4 || NW == 8 || NW == 16, "rows per tile");
+    const int V = p.V, GT = L.gt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = lane / CELLS, c = lane - gl * CELLS;
     const unsigned lt = (1u << lane) - 1u;
     float4* wts = reinterpret_cast<float4*>(sm + L.wts);
     int2* ent = reinterpret_cast<int2*>(sm + L.ent);
-    unsigned* mask = reinterpret_cast<unsigned*>(sm + L.mask);
-    int4* stg = reinterpret_cast<int4*>(sm + L.stg);
+    unsigned* wst = reinterpret_cast<unsigned*>(sm + L.wst);
+    int4* sdesc = reinterpret_cast<int4*>(sm + L.sdesc);
     int2* ops = reinterpret_cast<int2*>(sm + L.ops);
     int* misc = reinterpret_cast<int*>(sm + L.misc);
     float* sH = reinterpret_cast<float*>(sm + L.sH);
     int* xy = reinterpret_cast<int*>(sm + L.xy);
-    int* yt = reinterpret_cast<int*>(sm + L.yt);        // [v] lo, [V + v] hi
-    int* yr = reinterpret_cast<int*>(sm + L.yr);        // [r * V + v] lo, [R * V + ...] hi
-    int* tsp = reinterpret_cast<int*>(sm + L.tsp);      // [(v * 32 + row) * 2] lo, + 1 hi
-    int* rsp = reinterpret_cast<int*>(sm + L.rsp);      // [((r * V + v) * 12 + row) * 2]
-    unsigned* trow = reinterpret_cast<unsigned*>(sm + L.trow);
-    unsigned* rrow = reinterpret_cast<unsigned*>(sm + L.rrow);
-    int* vinfo = reinterpret_cast<int*>(sm + L.vinfo);  // [v * 8 + {kind, stages, ops, bytes, row mask}]
-    int* rinfo = reinterpret_cast<int*>(sm + L.rinfo);  // [(r * V + v) * 4 + {kind, ops, bytes, real reloads}]
+    unsigned* mask = reinterpret_cast<unsigned*>(sm + L.mask);
+    int* yr = reinterpret_cast<int*>(sm + L.yr);        // [r * V + v] lo, [NW * V + ...] hi
+    int* rsp = reinterpret_cast<int*>(sm + L.rsp);      // [((r * V + v) * 12 + row) * 2] lo, + 1 hi
+    unsigned* gtab = reinterpret_cast<unsigned*>(sm + L.gtab);
+    int4* ginfo = reinterpret_cast<int4*>(sm + L.ginfo);
+    int* vst = reinterpret_cast<int*>(sm + L.vst);      // [(v * NW + k) * 8 + ...]
+    int* vcnt = reinterpret_cast<int*>(sm + L.vcnt);    // [v * 2 + {stages, ops}]
+    int* soff = reinterpret_cast<int*>(sm + L.soff);
     constexpr int IMAX = 0x7fffffff, IMIN = (int)0x80000000;
 
     // ---- P0: homographies (geometry.py:60-63), scratch initialisation -------------------------------------------
@@ -148,12 +156,10 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
 #pragma unroll
         for (int q = 0; q < 3; ++q) reinterpret_cast<float4*>(sH + 12 * tid)[q] = make_float4(H[3 * q], H[3 * q + 1], H[3 * q + 2], 0.0f);
     }
-    for (int z = tid; z < V; z += NT) { yt[z] = IMAX; yt[V + z] = IMIN; }
-    for (int z = tid; z < V * kStRowsT; z += NT) { tsp[2 * z] = IMAX; tsp[2 * z + 1] = IMIN; }
     for (int z = tid; z < NW * V * kStRowsR; z += NT) { rsp[2 * z] = IMAX; rsp[2 * z + 1] = IMIN; }
     __syncthreads();
 
-    // ---- P1: project this warp's row; weights, masks, row-level texel-row range and spans --------------------------
+    // ---- P1: project this warp's row; weights, masks, the row's texel-row range and spans per view -----------------
     const int r = warp, i = i0 + r;
     unsigned all_seen = CMASK;
     for (int v0 = 0; v0 < V; v0 += GPW) {
@@ -195,7 +201,6 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
                 mask[r * V + v] = ((seen_b >> shift) & CMASK) | (((reload_b >> shift) & CMASK) << 16);
                 yr[r * V + v] = ymin;
                 yr[NW * V + r * V + v] = ymax;
-                if (ymin <= ymax) { atomicMin(yt + v, ymin); atomicMax(yt + V + v, ymax); }
             }
             if (real && ymax - ymin + 2 <= kStRowsR) {
                 int* sp = rsp + ((r * V + v) * kStRowsR + (t.y0 - ymin)) * 2;
@@ -212,168 +217,199 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
     if (lane == 0) misc[1 + r] = (int)all_seen;
     __syncthreads();
 
-    // ---- P2: tile-level spans ---------------------------------------------------------------------------------------
-    for (int v0 = 0; v0 < V; v0 += GPW) {
-        const int v = v0 + gl;
-        if (v < V) {
-            const int q = xy[(r * V + v) * CELLS + c];
-            const int x0 = (int)(short)(q & 0xffff), y0 = q >> 16;
-            const bool real = ((mask[r * V + v] >> c) & 1u) && x0 != -2;
-            const int lo = yt[v], hi = yt[V + v];
-            if (real && hi - lo + 2 <= kStRowsT) {
-                int* sp = tsp + (v * kStRowsT + (y0 - lo)) * 2;
-                atomicMin(sp, x0); atomicMax(sp + 1, x0 + 1);
-                atomicMin(sp + 2, x0); atomicMax(sp + 3, x0 + 1);
-            }
-        }
-    }
-    __syncthreads();
-
-    // ---- P3: plan.  Warp w owns views w, w + NW, ...: lane = texel row of the view's range ---------------------------
-    auto plan_rows = [&](const int* sp, int nrows, bool ok_in, unsigned* out, int& nops, int& bytes) -> bool {
-        // sp: spans of the `nrows` texel rows; out[row] = slot offset in texels | map << 12 | lo << 16 (map 15: no copy)
-        int lo = IMAX, hi = IMIN;
-        if (ok_in && lane < nrows) { lo = sp[2 * lane]; hi = sp[2 * lane + 1]; }
-        const int w = (lo <= hi) ? hi - lo + 1 : 0;
-        const int idx = w ? st_width_index(w) : -1;
-        const bool bad = w && idx < 0;
-        const int wq = (w && idx >= 0) ? st_width(idx) : 0;
-        int incl = wq;
-#pragma unroll
-        for (int o = 1; o < 32; o *= 2) {
-            const int u = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += u;
-        }
-        const int total = __shfl_sync(0xffffffffu, incl, 31);
-        const bool ok = ok_in && !__any_sync(0xffffffffu, bad) && total * 512 <= S;
-        if (ok && lane < nrows) out[lane] = (unsigned)(incl - wq) | ((unsigned)(w ? idx : 15) << 12) | ((unsigned)(lo & 0xffff) << 16);
-        nops = __popc(__ballot_sync(0xffffffffu, w > 0));
-        bytes = total * 512;
-        return ok;
-    };
+    // ---- P3: group the rows of every view into stages.  Warp w owns views w, w + NW, ...; lane = texel row -------------
     for (int v = warp; v < V; v += NW) {
-        const int tlo = yt[v], thi = yt[V + v];
-        const bool tile_range = tlo <= thi && thi - tlo + 2 <= kStRowsT;
-        const unsigned rowmask = __ballot_sync(0xffffffffu, lane < NW && (mask[(lane < NW ? lane : 0) * V + v] & 0xffffu) != 0);
-        int nops = 0, bytes = 0;
-        const bool tile_ok = plan_rows(tsp + v * kStRowsT * 2, kStRowsT, tile_range, trow + v * kStRowsT, nops, bytes);
-        int kind = ST_NONE, nst = 0;
-        if (tile_ok) {
-            kind = ST_TILE; nst = 1;
-        } else if (rowmask) {
-            kind = ST_ROWS; nops = 0; bytes = 0;
-            for (int rr = 0; rr < NW; ++rr) {
-                int* ri = rinfo + (rr * V + v) * 4;
-                if (!((rowmask >> rr) & 1u)) { if (lane == 0) ri[0] = ST_NONE; continue; }
-                const int rlo = yr[rr * V + v], rhi = yr[NW * V + rr * V + v];
-                const bool any_real = rlo <= rhi;
-                int rn = 0, rb = 0;
-                const bool row_ok = plan_rows(rsp + (rr * V + v) * kStRowsR * 2, kStRowsR, any_real && rhi - rlo + 2 <= kStRowsR,
-                                              rrow + (rr * V + v) * kStRowsR, rn, rb);
-                // reloads of cells that have texels (a non-finite sample position has none)
-                const unsigned m = mask[rr * V + v];
-                const int q = xy[(rr * V + v) * CELLS + (lane & (CELLS - 1))];
-                const unsigned rrl = __ballot_sync(0xffffffffu, lane < CELLS && ((m >> (16 + lane)) & 1u) && (int)(short)(q & 0xffff) != -2);
-                int rk = ST_SPANS;
-                if (!any_real) { rn = 0; rb = 0; }                       // only NaN cells: a stage without copies
-                else if (!row_ok) { rk = ST_BLOCKS; rn = __popc(rrl); rb = rn * 2048; }
-                if (lane == 0) { ri[0] = rk; ri[1] = rn; ri[2] = rb; ri[3] = (int)rrl; }
-                ++nst; nops += rn;
+        const bool rl = lane < NW;
+        const int my_lo = rl ? yr[lane * V + v] : IMAX, my_hi = rl ? yr[NW * V + lane * V + v] : IMIN;
+        const unsigned rowseen = __ballot_sync(0xffffffffu, rl && (mask[(rl ? lane : 0) * V + v] & 0xffffu) != 0);
+        const unsigned realrows = __ballot_sync(0xffffffffu, rl && my_lo <= my_hi);
+        const unsigned spanable = __ballot_sync(0xffffffffu, rl && my_lo <= my_hi && my_hi - my_lo + 2 <= kStRowsR);
+        int nst_v = 0, nops_v = 0, gbase = 0;
+        for (int r0 = 0; r0 < NW;) {
+            int len = NW;
+            while (len > 1 && (r0 & (len - 1))) len >>= 1;
+            for (;;) {
+                const unsigned gm = ((len >= 32 ? 0u : (1u << len)) - 1u) << r0;
+                const unsigned gseen = rowseen & gm, greal = realrows & gm;
+                if (!gseen) break;                                         // no row of the group samples this view: no stage
+                if (len > 1 && (greal & ~spanable)) { len >>= 1; continue; }  // a row too tall for spans: split
+                int kind = ST_SPANS, nops = 0, bytes = 0, gmin = 0, nrows = 0;
+                if (greal && (len > 1 || (spanable >> r0) & 1u)) {
+                    // merged spans of the group's rows: texel row `lane` of the group
+                    int a = (greal >> lane) & 1u ? my_lo : IMAX, z = (greal >> lane) & 1u ? my_hi : IMIN;
+#pragma unroll
+                    for (int o = 1; o < 32; o *= 2) {
+                        a = min(a, __shfl_xor_sync(0xffffffffu, a, o));
+                        z = max(z, __shfl_xor_sync(0xffffffffu, z, o));
+                    }
+                    gmin = a;
+                    nrows = z - a + 2;
+                    bool ok = nrows <= kStRowsG;
+                    int lo = IMAX, hi = IMIN;
+                    if (ok) {
+                        for (unsigned rem = greal; rem;) {
+                            const int rr = __ffs(rem) - 1;
+                            rem &= rem - 1;
+                            const int idx = lane - (__shfl_sync(0xffffffffu, my_lo, rr) - gmin);
+                            if (idx >= 0 && idx < kStRowsR) {
+                                const int* sp = rsp + ((rr * V + v) * kStRowsR + idx) * 2;
+                                lo = min(lo, sp[0]); hi = max(hi, sp[1]);
+                            }
+                        }
+                    }
+                    const int w = (lo <= hi) ? hi - lo + 1 : 0;
+                    const int widx = w ? st_width_index(w) : -1;
+                    const bool bad = w && widx < 0;
+                    const int wq = (w && widx >= 0) ? st_width(widx) : 0;
+                    int incl = wq;
+#pragma unroll
+                    for (int o = 1; o < 32; o *= 2) {
+                        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += u;
+                    }
+                    const int total = __shfl_sync(0xffffffffu, incl, 31);
+                    ok = ok && !__any_sync(0xffffffffu, bad) && total * 512 <= cap;
+                    if (!ok) {
+                        if (len > 1) { len >>= 1; continue; }
+                        kind = ST_BLOCKS;
+                    } else {
+                        if (lane < nrows) gtab[v * GT + gbase + lane] = (unsigned)(incl - wq) | ((unsigned)(w ? widx : 15) << 12) | ((unsigned)(lo & 0xffff) << 16);
+                        nops = __popc(__ballot_sync(0xffffffffu, w > 0));
+                        bytes = total * 512;
+                    }
+                } else if (greal) {
+                    kind = ST_BLOCKS;                                      // a single row too tall for spans
+                }
+                // (a group whose rows only hold non-finite sample positions: a stage without copies, kind SPANS, 0 bytes)
+                unsigned rrl = 0;
+                if (kind == ST_BLOCKS) {
+                    // reloads of cells that have texels (a non-finite sample position has none): one [2 x 2] box each
+                    const unsigned m = mask[r0 * V + v];
+                    const int q = xy[(r0 * V + v) * CELLS + (lane & (CELLS - 1))];
+                    rrl = __ballot_sync(0xffffffffu, lane < CELLS && ((m >> (16 + lane)) & 1u) && (int)(short)(q & 0xffff) != -2);
+                    nops = __popc(rrl);
+                    bytes = nops * 2048;
+                    nrows = 0;
+                }
+                if (lane < NW && ((gseen >> lane) & 1u)) ginfo[lane * V + v] = make_int4(kind, gbase, gmin, (int)rrl);
+                if (lane == 0) {
+                    int* st = vst + (v * NW + nst_v) * 8;
+                    st[0] = (int)gseen; st[1] = bytes; st[2] = nops; st[3] = kind; st[4] = gbase; st[5] = gmin; st[6] = nrows; st[7] = r0;
+                }
+                gbase += nrows;
+                ++nst_v;
+                nops_v += nops;
+                break;
             }
+            r0 += len;
         }
-        if (lane == 0) {
-            int* vi = vinfo + v * 8;
-            vi[0] = kind; vi[1] = nst; vi[2] = nops; vi[3] = bytes; vi[4] = (int)rowmask;
-        }
+        if (lane == 0) { vcnt[2 * v] = nst_v; vcnt[2 * v + 1] = nops_v; }
     }
     __syncthreads();
 
     // ---- P4: emit the stage list and the row copies (views ascending: the accumulation order) --------------------
+    int nst;
     {
         int my_st = 0, my_op = 0;  // lane = view: exclusive prefix sums of stages and ops
-        if (lane < V) { my_st = vinfo[lane * 8 + 1]; my_op = vinfo[lane * 8 + 2]; }
+        if (lane < V) { my_st = vcnt[2 * lane]; my_op = vcnt[2 * lane + 1]; }
         int inc_st = my_st, inc_op = my_op;
 #pragma unroll
         for (int o = 1; o < 32; o *= 2) {
             const int a = __shfl_up_sync(0xffffffffu, inc_st, o), bq = __shfl_up_sync(0xffffffffu, inc_op, o);
             if (lane >= o) { inc_st += a; inc_op += bq; }
         }
-        if (tid == 31) misc[0] = inc_st;  // stages of the tile
+        nst = __shfl_sync(0xffffffffu, inc_st, 31);
+        if (tid == 0) misc[0] = nst;
         for (int v = warp; v < V; v += NW) {
             int s = __shfl_sync(0xffffffffu, inc_st - my_st, v), o = __shfl_sync(0xffffffffu, inc_op - my_op, v);
-            const int* vi = vinfo + v * 8;
-            const int kind = vi[0];
-            if (kind == ST_TILE) {
-                const int tlo = yt[v];
-                const unsigned e = trow[v * kStRowsT + lane];
-                const int idx = (e >> 12) & 15;
-                const unsigned has = __ballot_sync(0xffffffffu, idx != 15);
-                if (idx != 15) {
-                    const int x = (int)(short)(e >> 16), y = tlo + lane;
-                    ops[o + __popc(has & lt)] = make_int2((x & 0xffff) | (y << 16), (int)((e & 0xfffu) * 32u) | (idx << 16));
-                }
-                if (lane == 0) stg[s] = make_int4(v, vi[4], vi[3], o | (vi[2] << 16));
-            } else if (kind == ST_ROWS) {
-                const unsigned rowmask = (unsigned)vi[4];
-                for (int rr = 0; rr < NW; ++rr) {
-                    if (!((rowmask >> rr) & 1u)) continue;
-                    const int* ri = rinfo + (rr * V + v) * 4;
-                    const int rk = ri[0], rn = ri[1];
-                    if (rk == ST_SPANS && rn > 0) {
-                        const int rlo = yr[rr * V + v];
-                        unsigned e = 15u << 12;
-                        if (lane < kStRowsR) e = rrow[(rr * V + v) * kStRowsR + lane];
-                        const int idx = (e >> 12) & 15;
-                        const unsigned has = __ballot_sync(0xffffffffu, idx != 15);
-                        if (idx != 15) {
-                            const int x = (int)(short)(e >> 16), y = rlo + lane;
-                            ops[o + __popc(has & lt)] = make_int2((x & 0xffff) | (y << 16), (int)((e & 0xfffu) * 32u) | (idx << 16));
-                        }
-                    } else if (rk == ST_BLOCKS) {
-                        const unsigned rrl = (unsigned)ri[3];
-                        if (lane < CELLS && ((rrl >> lane) & 1u)) {
-                            const int q = xy[(rr * V + v) * CELLS + lane];
-                            ops[o + __popc(rrl & lt)] = make_int2(q, (__popc(rrl & lt) * 128) | (kStBlockMap << 16));
-                        }
+            const int nv = __shfl_sync(0xffffffffu, my_st, v);
+            for (int k = 0; k < nv; ++k) {
+                const int* st = vst + (v * NW + k) * 8;
+                const int nops = st[2], kind = st[3];
+                if (kind == ST_SPANS) {
+                    unsigned e = 15u << 12;
+                    if (lane < st[6]) e = gtab[v * GT + st[4] + lane];
+                    const int widx = (e >> 12) & 15;
+                    const unsigned has = __ballot_sync(0xffffffffu, widx != 15);
+                    if (widx != 15) {
+                        const int x = (int)(short)(e >> 16), y = st[5] + lane;
+                        ops[o + __popc(has & lt)] = make_int2((x & 0xffff) | (y << 16), (int)((e & 0xfffu) * 32u) | (widx << 16));
                     }
-                    if (lane == 0) stg[s] = make_int4(v, (int)(1u << rr), ri[2], o | (rn << 16));
-                    ++s; o += rn;
+                } else {
+                    const unsigned rrl = (unsigned)ginfo[st[7] * V + v].w;
+                    if (lane < CELLS && ((rrl >> lane) & 1u))
+                        ops[o + __popc(rrl & lt)] = make_int2(xy[(st[7] * V + v) * CELLS + lane], (__popc(rrl & lt) * 128) | (kStBlockMap << 16));
                 }
+                if (lane == 0) sdesc[s + k] = make_int4(st[1], 0, o | (nops << 16), v | (st[0] << 8));
+                o += nops;
             }
         }
     }
-    // ---- P5: every (row, view, cell)'s tap offsets inside its stage's slot ------------------------------------------
+    // ---- P5: every (row, view, cell)'s tap offsets inside its stage --------------------------------------------------
     for (int v0 = 0; v0 < V; v0 += GPW) {
         const int v = v0 + gl;
         if (v < V) {
             const int e = (r * V + v) * CELLS + c;
             const int q = xy[e];
             const int x0 = (int)(short)(q & 0xffff), y0 = q >> 16;
-            const bool real = ((mask[r * V + v] >> c) & 1u) && x0 != -2;
+            const unsigned m = mask[r * V + v];
+            const bool real = ((m >> c) & 1u) && x0 != -2;
             int2 o = make_int2(0, 0);
             if (real) {
-                const int kind = vinfo[v * 8];
-                if (kind == ST_TILE) {
-                    const unsigned* tr = trow + v * kStRowsT + (y0 - yt[v]);
+                const int4 gi = ginfo[r * V + v];
+                if (gi.x == ST_SPANS) {
+                    const unsigned* tr = gtab + v * GT + gi.y + (y0 - gi.z);
                     const unsigned a = tr[0], bq = tr[1];
                     o.x = ((int)(a & 0xfffu) + x0 - (int)(short)(a >> 16)) * 512;
                     o.y = ((int)(bq & 0xfffu) + x0 - (int)(short)(bq >> 16)) * 512;
                 } else {
-                    const int* ri = rinfo + (r * V + v) * 4;
-                    if (ri[0] == ST_SPANS) {
-                        const unsigned* tr = rrow + (r * V + v) * kStRowsR + (y0 - yr[r * V + v]);
-                        const unsigned a = tr[0], bq = tr[1];
-                        o.x = ((int)(a & 0xfffu) + x0 - (int)(short)(a >> 16)) * 512;
-                        o.y = ((int)(bq & 0xfffu) + x0 - (int)(short)(bq >> 16)) * 512;
-                    } else {
-                        const unsigned rrl = (unsigned)ri[3];
-                        const int k = __popc(rrl & ((2u << c) - 1u)) - 1;  // the block of the last reload at or before this cell
-                        o.x = k * 2048;
-                        o.y = k * 2048 + 1024;
-                    }
+                    const int k = __popc((unsigned)gi.w & ((2u << c) - 1u)) - 1;  // the block of the last reload at or before this cell
+                    o.x = k * 2048;
+                    o.y = k * 2048 + 1024;
                 }
             }
             ent[e] = o;
+        }
+    }
+    __syncthreads();
+
+    // ---- P6: static places in the ring and predecessor distances (warp 0); every warp's per-stage words ---------------
+    for (int s = lane; s < nst; s += 32) {
+        const int w = sdesc[s].w;
+        const int v = w & 0xff;
+        const unsigned m = mask[r * V + v];
+        const bool mine = ((w >> (8 + r)) & 1) && (m & 0xffffu);
+        wst[r * L.nst_max + s] = mine ? ((m & 0xffu) | (((m >> 16) & 0xffu) << 8) | ((unsigned)v << 24)) : 0u;
+    }
+    if (warp == 0) {
+        if (lane == 0) {
+            int pos = 0;
+            for (int s = 0; s < nst; ++s) {
+                const int bts = (sdesc[s].x + 127) & ~127;
+                if (pos + bts > ring_bytes) pos = 0;      // wrap: a stage is contiguous
+                soff[s] = pos;
+                pos += bts;
+            }
+        }
+        __syncwarp();
+        for (int s = 0; s < nst; ++s) {
+            const int so = soff[s], sb = sdesc[s].x;
+            int dback = nst;                              // the same stage, one item earlier
+            if (sb > 0) {
+                for (int k0 = 1; k0 < nst && dback == nst; k0 += 32) {
+                    const int k = k0 + lane;
+                    bool hit = false;
+                    if (k < nst) {
+                        int q = s - k;
+                        if (q < 0) q += nst;
+                        const int qo = soff[q], qb = sdesc[q].x;
+                        hit = qb > 0 && qo < so + sb && so < qo + qb;
+                    }
+                    const unsigned hb = __ballot_sync(0xffffffffu, hit);
+                    if (hb) dback = k0 + __ffs(hb) - 1;
+                }
+            }
+            if (lane == 0) sdesc[s].y = (so >> 7) | (dback << 16);
         }
     }
     // the scratch arrays were written and read through the generic proxy; the TMA unit (async proxy) writes the ring next
@@ -384,15 +420,17 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views with the zeros of views that miss a cell
 // (fusion.py:22).  PROBE (timing aid, results are NOT the fusion): 1 = no TMA copies are issued.
+// ring_bytes: size of the stage ring; cap: largest stage (bytes); lag: a stage is armed `lag` stages after its
+// predecessor in the ring was walked (1 = as soon as possible: the arming warp then waits for the slowest warp).
 template <typename TIn, typename TOut, int NW, int MAXREG, int KMODE, int PROBE = 0>
-__global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, int fpc, int S, int D, int LOOK, const __grid_constant__ StagedMaps maps,
-                                                                 unsigned char* dump) {
+__global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, int fpc, int ring_bytes, int cap, int lag,
+                                                                 const __grid_constant__ StagedMaps maps, unsigned char* dump) {
     using VT = VecTraits<TIn>;
     constexpr int VE = VT::VE, P = VT::P, CELLS = kStCells, NT = NW * 32;
     constexpr int ILP = (P > 2) ? 2 : P;
     extern __shared__ __align__(128) unsigned char smem_st[];
     const int V = p.V;
-    const StagedSmem L(V, NW, S, D);
+    const StagedSmem L(V, NW);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
     const int ty = blockIdx.x / p.tiles_x, tx = blockIdx.x - ty * p.tiles_x;
@@ -404,21 +442,21 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
     const float Vf = (float)V;
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_st);
     const uint32_t s_wts = sbase + L.wts + r * V * CELLS * 16, s_ent = sbase + L.ent + r * V * CELLS * 8;
-    const uint32_t s_mask = sbase + L.mask + r * V * 4, s_stg = sbase + L.stg, s_ops = sbase + L.ops;
-    const uint32_t s_full = sbase + L.bars, s_empty = s_full + D * 8;
+    const uint32_t s_wst = sbase + L.wst + r * L.nst_max * 4, s_sdesc = sbase + L.sdesc, s_ops = sbase + L.ops;
+    const uint32_t s_full = sbase + L.bars, s_empty = s_full + L.nst_max * 8;
     const uint32_t s_ring = sbase + L.ring;
     uint32_t lring = s_ring + lane * 16;
     asm volatile("" : "+r"(lring));
 
     for (int b = b0; b < b1;) {
-        if (b > b0) __syncthreads();  // every warp is done with the previous run's tables and slots
-        if (tid == 0) {
-            if (b > b0)
-                for (int s = 0; s < 2 * D; ++s) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(s_full + s * 8) : "memory");
-            for (int s = 0; s < D; ++s) { mbar_init(s_full + s * 8, 1); mbar_init(s_empty + s * 8, NW); }
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (b > b0) {
+            __syncthreads();  // every warp is done with the previous run's tables and ring
+            for (int s = tid; s < 2 * L.nst_max; s += NT) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(s_full + s * 8) : "memory");
+            __syncthreads();
         }
-        staged_build<NW, KMODE == KM_MAX>(p, L, smem_st, S, i0, j0, b);
+        for (int s = tid; s < L.nst_max; s += NT) { mbar_init(s_full + s * 8, 1); mbar_init(s_empty + s * 8, NW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        staged_build<NW, KMODE == KM_MAX>(p, L, smem_st, ring_bytes, cap, i0, j0, b);
         if (dump) {  // development aid (BEVIPM_ST_DUMP): the tables of every tile, no phase B
             unsigned char* dst = dump + ((size_t)blockIdx.z * gridDim.x + blockIdx.x) * (size_t)L.ring;
             for (int z = tid * 4; z < L.ring; z += NT * 4) *reinterpret_cast<int*>(dst + z) = *reinterpret_cast<const int*>(smem_st + z);
@@ -452,77 +490,76 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
         const int n_items = (e - b) * chunks;  // (frame, chunk) items, frame-major
         b = e;
         const int nst = __shfl_sync(0xffffffffu, lds4i(sbase + L.misc), 0);
-        const unsigned total = (unsigned)n_items * (unsigned)nst;  // stages of this run
+        const int total = n_items * nst;  // stages of this run
 
-        // arm stage m (warp-uniform; one elected lane talks to the TMA unit)
-        auto arm = [&](unsigned m) {
-            if (m >= total) return;
-            const unsigned use = m / (unsigned)D, slot = m - use * (unsigned)D;
-            if (use > 0) mbar_wait(s_empty + slot * 8, (use - 1u) & 1u);  // every warp has left the stage this slot held
-            const unsigned im = m / (unsigned)nst, sm_ = m - im * (unsigned)nst;
-            const unsigned fim = im / (unsigned)chunks, km = im - fim * (unsigned)chunks;
-            const int4 sd = lds16i(s_stg + sm_ * 16);
+        // arm stage ga = (item ia, stage sa): warp-uniform; one elected lane talks to the TMA unit
+        auto arm = [&](int ga, int sa, int ia) {
+            const int4 sd = lds16i(s_sdesc + sa * 16);
+            const int dback = sd.y >> 16;
+            if (ga - dback >= 0) {  // the last stage that used these bytes: every warp must have left it
+                int ps = sa - dback, pit = ia;
+                if (ps < 0) { ps += nst; --pit; }
+                mbar_wait(s_empty + ps * 8, (uint32_t)pit & 1u);
+            }
             if (elect_one()) {
-                const uint32_t bar = s_full + slot * 8, dst0 = s_ring + slot * (unsigned)S;
-                mbar_expect_tx(bar, sd.z);
+                const uint32_t bar = s_full + sa * 8, dst0 = s_ring + ((uint32_t)(sd.y & 0xffff) << 7);
+                mbar_expect_tx(bar, sd.x);
                 if (PROBE != 1) {
-                    const int o0 = sd.w & 0xffff, n = sd.w >> 16;
-                    const int c0 = (int)km * 32 * VE, bb = b_run + (int)fim;
+                    const int o0 = sd.z & 0xffff, n = sd.z >> 16;
+                    const int fim = ia / chunks, km = ia - fim * chunks;
+                    const int c0 = km * 32 * VE, bb = b_run + fim;
                     for (int q = 0; q < n; ++q) {
                         const int2 op = lds8i(s_ops + (o0 + q) * 8);
                         const int x = (int)(short)(op.x & 0xffff), y = op.x >> 16;
-                        tma_load_5d(dst0 + (uint32_t)(op.y & 0xffff) * 16u, &maps.m[op.y >> 16], c0, x, y, sd.x, bb, bar);
+                        tma_load_5d(dst0 + (uint32_t)(op.y & 0xffff) * 16u, &maps.m[op.y >> 16], c0, x, y, sd.w & 0xff, bb, bar);
                     }
                 } else {
-                    asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(sd.z) : "memory");
+                    asm volatile("mbarrier.complete_tx.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(sd.x) : "memory");
                 }
             }
             __syncwarp();
         };
+        // when stage ga is due: `lag` stages after its predecessor in the ring, at the latest when it is walked itself
+        auto due = [&](int ga, int sa) { return ga < total ? min(ga, ga - (lds4i(s_sdesc + sa * 16 + 4) >> 16) + lag) : 0x7fffffff; };
 
-        if (nst > 0 && warp == 0)
-            for (int m = 0; m < LOOK; ++m) arm((unsigned)m);
-
-        unsigned n = 0;       // stage counter of the run
-        int slot = 0;         // n % D
-        unsigned phase = 0;   // (n / D) & 1
-        int duty = 0;         // n % NW
+        int ga = 0, sa = 0, ia = 0;   // next stage to arm: global index, stage, item
+        int at = nst > 0 ? due(0, 0) : 0x7fffffff;
+        int g = 0;                    // stage being walked (global index)
+        int duty = 0;                 // g % NW
         int fi_c = 0, k_c = 0;
+        float2 cur[4][P];
+#pragma unroll
+        for (int tap = 0; tap < 4; ++tap)
+#pragma unroll
+            for (int q = 0; q < P; ++q) cur[tap][q] = make_float2(0.0f, 0.0f);
         for (int it = 0; it < n_items; ++it) {
             float2 acc[CELLS][P];
 #pragma unroll
             for (int c = 0; c < CELLS; ++c)
 #pragma unroll
                 for (int q = 0; q < P; ++q) acc[c][q] = (KMODE == KM_MAX) ? make_float2(-INFINITY, -INFINITY) : make_float2(0.0f, 0.0f);
-            float2 cur[4][P];
-#pragma unroll
-            for (int tap = 0; tap < 4; ++tap)
-#pragma unroll
-                for (int q = 0; q < P; ++q) cur[tap][q] = make_float2(0.0f, 0.0f);
+            const uint32_t par = (uint32_t)it & 1u;
 
             for (int s = 0; s < nst; ++s) {
-                if (duty == warp) arm(n + (unsigned)LOOK);
-                const int4 sd = lds16i(s_stg + s * 16);
-                const int v = __shfl_sync(0xffffffffu, sd.x, 0);
-                const unsigned m = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_mask + 4 * v), 0);
-                const bool mine = ((__shfl_sync(0xffffffffu, sd.y, 0) >> r) & 1) && (m & 0xffffu);
-                // Every warp waits for every stage, also the ones that hold nothing for its row: a warp that skipped the wait
-                // could run a whole ring revolution ahead, where the parity of its next wait on this slot would alias an
-                // older phase (and its `empty` arrival would be counted for the stage before).
-                mbar_wait(s_full + slot * 8, phase);  // the stage's bytes have landed
-                if (mine) {
-                    const uint32_t sb = lring + (uint32_t)slot * (uint32_t)S;
+                while (at <= g) {  // every warp follows the schedule; the warp on duty issues
+                    if (duty == warp) arm(ga, sa, ia);
+                    ++ga;
+                    if (++sa == nst) { sa = 0; ++ia; }
+                    at = due(ga, sa);
+                }
+                const unsigned m = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_wst + s * 4), 0);  // seen | reload << 8 | view << 24
+                mbar_wait(s_full + s * 8, par);  // the stage's bytes have landed
+                if (m) {
+                    const int v = (int)(m >> 24);
+                    const uint32_t sb = lring + (((uint32_t)lds4i(s_sdesc + s * 16 + 4) & 0xffffu) << 7);
                     const uint32_t wv = s_wts + v * (CELLS * 16), ev = s_ent + v * (CELLS * 8);
                     float4 wn = lds16f(wv);
-                    bool rl = (m >> 16) & 1u;
 #pragma unroll
                     for (int c = 0; c < CELLS; ++c) {
                         const float4 w = wn;
                         if (c + 1 < CELLS) wn = lds16f(wv + (c + 1) * 16);
-                        const bool seen = (m >> c) & 1u;
-                        const bool rl_now = rl;
-                        if (c + 1 < CELLS) rl = (m >> (17 + c)) & 1u;
-                        if (rl_now) {  // the row leaves the block held in `cur`
+                        if (!((m >> c) & 1u)) continue;  // the view does not see this cell (warp-uniform)
+                        if ((m >> (8 + c)) & 1u) {       // the row leaves the block held in `cur`
                             const int2 o = lds8i(ev + c * 8);
                             const uint32_t a0 = sb + (uint32_t)o.x, a1 = sb + (uint32_t)o.y;
                             uint4 nxt[4];
@@ -544,23 +581,21 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
 #pragma unroll
                             for (int q = 0; q < ILP; ++q) sv[q] = __ffma2_rn(cur[3][q0 + q], make_float2(w.w, w.w), sv[q]);
 #pragma unroll
-                            for (int q = 0; q < ILP; ++q)
-                                if (seen) {
-                                    if constexpr (KMODE == KM_MAX) {  // fusion.py:22, NaN propagates like torch.max
-                                        float2& mx = acc[c][q0 + q];
-                                        mx.x = max_nan(mx.x, sv[q].x);
-                                        mx.y = max_nan(mx.y, sv[q].y);
-                                    } else {
-                                        acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
-                                    }
+                            for (int q = 0; q < ILP; ++q) {
+                                if constexpr (KMODE == KM_MAX) {  // fusion.py:22, NaN propagates like torch.max
+                                    float2& mx = acc[c][q0 + q];
+                                    mx.x = max_nan(mx.x, sv[q].x);
+                                    mx.y = max_nan(mx.y, sv[q].y);
+                                } else {
+                                    acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
                                 }
+                            }
                         }
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(s_empty + slot * 8);  // this warp is done with the slot
-                ++n;
-                if (++slot == D) { slot = 0; phase ^= 1u; }
+                if (lane == 0) mbar_arrive(s_empty + s * 8);  // this warp is done with the stage's bytes
+                ++g;
                 if (++duty == NW) duty = 0;
             }
 
