@@ -31,15 +31,16 @@ def layout(V, R):
     L["ent"] = o; o += R * V * CELLS * 8
     L["wst"] = o; o += up(R * L["nst_max"] * 4, 16)
     L["sdesc"] = o; o += L["nst_max"] * 16
+    L["sched"] = o; o += 256 * 8
     L["ops"] = o; o += L["max_ops"] * 8
-    L["bars"] = o; o += up(2 * L["nst_max"] * 8, 16)
+    L["bars"] = o; o += 2 * 64 * 8
     L["misc"] = o; o += 128
     L["sH"] = o; o += V * 48
     L["ring"] = up(o, 128)
     return L
 
 
-def check(path, x0, y0, Hf, Wf, verbose=False):
+def check(path, x0, y0, Hf, Wf, B_frames=1, verbose=False):
     raw = open(path, "rb").read()
     V, NW, ring_bytes, cap, ring, gx, gz, tiles_x, tiles_y, fpc, Hb, Wb, Hf2, Wf2, C, es = struct.unpack("16i", raw[:64])
     L = layout(V, NW)
@@ -65,14 +66,12 @@ def check(path, x0, y0, Hf, Wf, verbose=False):
         last_v = -1
         for s, (nbytes, yw, opw, vw) in enumerate(sdesc):
             v, rowmask = vw & 0xff, (vw >> 8) & 0xffff
-            off, dback = (yw & 0xffff) << 7, yw >> 16
-            regions.append((off, nbytes, dback))
             o0, n = opw & 0xffff, opw >> 16
             if v < last_v:
                 print(f"cta {cta}: stage {s} view {v} after view {last_v}"); errs += 1
             last_v = v
-            if nbytes > cap or off + nbytes > ring_bytes:
-                print(f"cta {cta} stage {s}: {nbytes} bytes at {off} (cap {cap}, ring {ring_bytes})"); errs += 1
+            if nbytes > cap:
+                print(f"cta {cta} stage {s}: {nbytes} bytes (cap {cap})"); errs += 1
             tm = {}
             tot = 0
             isblk = False
@@ -104,18 +103,27 @@ def check(path, x0, y0, Hf, Wf, verbose=False):
                     if (r, v) in stage_of:
                         print(f"cta {cta}: (row {r}, view {v}) in two stages"); errs += 1
                     stage_of[(r, v)] = s
-        # ring places: nothing among the dback-1 stages before s (cyclically) may overlap s; stage s-dback does (or dback == nst)
-        for s, (off, nb, dback) in enumerate(regions):
-            if nb == 0:
-                continue
-            for k in range(1, nst + 1):
-                q = (s - k) % nst
-                qo, qb, _ = regions[q]
-                hit = (qb > 0 and qo < off + nb and off < qo + qb) or k == nst
-                if hit:
-                    if k != dback:
-                        print(f"cta {cta} stage {s}: first overlap {k} stages back, table says {dback}"); errs += 1
-                    break
+        # the copy schedule: places inside the ring, nothing among the `back - 1` stages before an entry (cyclically) may
+        # overlap it, predecessors in non-decreasing order
+        chunks = -(-(C * es) // 512)
+        n_items = min(fpc, B_frames) * chunks
+        if nst:
+            PL = max(1, min(n_items, 256 // nst)) * nst
+            sched = i32(L["sched"], 2 * 256).reshape(-1, 2)[:PL]
+            prev_pred = None
+            for q in range(PL):
+                off, back, nb = (int(sched[q, 0]) & 0xffff) << 7, int(sched[q, 0]) >> 16, int(sched[q, 1])
+                if nb != int(sdesc[q % nst][0]) or off + nb > ring_bytes or back < 1:
+                    print(f"cta {cta} schedule {q}: bytes {nb} (stage {int(sdesc[q % nst][0])}) at {off}, back {back}"); errs += 1
+                for k in range(1, min(back, PL)):
+                    q2 = (q - k) % PL
+                    qo, qb = (int(sched[q2, 0]) & 0xffff) << 7, int(sched[q2, 1])
+                    if nb > 0 and qb > 0 and qo < off + nb and off < qo + qb:
+                        print(f"cta {cta} schedule {q}: overlaps entry {q2}, only {k} back (table says {back})"); errs += 1
+                        break
+                if prev_pred is not None and q - back < prev_pred:
+                    print(f"cta {cta} schedule {q}: predecessor {q - back} older than the one before ({prev_pred})"); errs += 1
+                prev_pred = q - back
         for r in range(NW):
             i = i0 + r
             for v in range(V):
@@ -175,7 +183,7 @@ def main():
     fin = np.isfinite(ix) & np.isfinite(iy)
     x0 = np.where(fin, np.floor(np.where(fin, ix, 0)), -2).clip(-2, Wf).astype(np.int64)
     y0 = np.where(fin, np.floor(np.where(fin, iy, 0)), -2).clip(-2, Hf).astype(np.int64)
-    errs, kinds, tex = check(path, x0, y0, Hf, Wf, verbose="-v" in sys.argv)
+    errs, kinds, tex = check(path, x0, y0, Hf, Wf, B_frames=B, verbose="-v" in sys.argv)
     seen = ((x0 >= -1) & (x0 <= Wf - 1) & (y0 >= -1) & (y0 <= Hf - 1)).sum()
     print(f"variant {variant} shape {(V, C, Hf, Wf, Hb, Wb, B)}: {errs} errors; stages {kinds}; staged texels per item {tex} "
           f"= {tex / max(seen, 1):.3f} per cell-view")

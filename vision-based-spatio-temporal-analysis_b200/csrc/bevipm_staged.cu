@@ -147,6 +147,7 @@ template <typename TIn, typename TOut, int NW>
 int launch_mode(const FwdParams& p, int cps, int probe, cudaStream_t st, char* err, size_t errlen) {
     if (p.mode == BEVIPM_MAX) return launch_t<TIn, TOut, NW, KM_MAX, 0>(p, cps, st, err, errlen);
     if (probe == 1) return launch_t<TIn, TOut, NW, KM_ACC, 1>(p, cps, st, err, errlen);
+    if (probe == 2) return launch_t<TIn, TOut, NW, KM_ACC, 2>(p, cps, st, err, errlen);
     return launch_t<TIn, TOut, NW, KM_ACC, 0>(p, cps, st, err, errlen);
 }
 

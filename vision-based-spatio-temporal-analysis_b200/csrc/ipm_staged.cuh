@@ -20,8 +20,8 @@
 //            The stages of one (frame, channel chunk) item get STATIC places in a ring of shared memory (sequential
 //            placement, wrapping to offset 0) and, each, the distance back to the last stage that used any of its
 //            bytes before: the whole copy schedule is periodic and known before the first copy is issued.
-//   phase B: the stage list is walked once per item.  Every stage has its own full (transaction bytes) / empty (one
-//            arrival per warp) mbarrier pair, phase parity = item parity.  The warps take turns at issuing: before
+//   phase B: the stage list is walked once per item.  Stage g of the run uses the full (transaction bytes) / empty (one
+//            arrival per warp) mbarrier pair g % 64, phase parity (g / 64) & 1.  The warps take turns at issuing: before
 //            stage g is walked, warp g % NW arms every stage whose predecessor in the ring was stage g - LAG or
 //            older (it waits for that predecessor's empty barrier first), so copies run as far ahead as the ring
 //            holds.  A warp owns one BEV row segment of 8 cells, keeps the 8 cells' accumulators in registers and
@@ -46,6 +46,9 @@ constexpr int kStRowsR = 12;     // texel rows one BEV row's spans may cover (el
 constexpr int kStNumW = 13;      // span widths with a tensor map of their own
 constexpr int kStBlockMap = 13;  // the [2 x 2] block map
 constexpr int kStNumMaps = 14;
+constexpr int kStSched = 256;     // entries of the copy schedule (one period)
+constexpr int kStBack = 64;       // how far back the schedule looks for a stage's predecessor in the ring; also the
+                                  // number of mbarrier pairs: stage g uses pair g % 64 with phase parity (g / 64) & 1
 
 // span width (texels, >= 1) -> index of the narrowest map that covers it; -1: wider than any map
 __host__ __device__ __forceinline__ int st_width_index(int w) {
@@ -67,8 +70,8 @@ struct alignas(64) StagedMaps {
 
 // shared-memory layout of one CTA: persistent tables, then the ring (phase A's scratch aliases the ring)
 struct StagedSmem {
-    int wts, ent, wst, sdesc, ops, bars, misc, sH, ring;           // persistent
-    int xy, mask, yr, rsp, gtab, ginfo, vst, vcnt, soff, scratch_end;  // scratch, inside the ring
+    int wts, ent, wst, sdesc, sched, ops, bars, misc, sH, ring;    // persistent
+    int xy, mask, yr, rsp, gtab, ginfo, vst, vcnt, scratch_end;    // scratch, inside the ring
     int nst_max, max_ops, gt;
     __host__ __device__ StagedSmem(int V, int R) {
         auto up = [](int x, int a) { return (x + a - 1) / a * a; };
@@ -79,9 +82,10 @@ struct StagedSmem {
         wts = o; o += R * V * kStCells * 16;             // float4 (nw, ne, sw, se) per (row, view, cell)
         ent = o; o += R * V * kStCells * 8;              // int2 (byte offset of the NW tap, of the SW tap) inside the stage
         wst = o; o += up(R * nst_max * 4, 16);           // per (row, stage): seen | reload << 8 | view << 24; 0 = not this row's
-        sdesc = o; o += nst_max * 16;                    // int4 {bytes, ring offset / 128 | dback << 16, first op | ops << 16, view}
+        sdesc = o; o += nst_max * 16;                    // int4 {bytes, -, first op | ops << 16, view | row mask << 8}
+        sched = o; o += kStSched * 8;                    // int2 {ring offset / 128 | stages back to the predecessor << 16, bytes} per stage of one period
         ops = o; o += max_ops * 8;                       // int2 {x | y << 16, stage offset / 16 | map << 16}
-        bars = o; o += up(2 * nst_max * 8, 16);          // full[nst_max], empty[nst_max]
+        bars = o; o += 2 * kStBack * 8;                  // full[64], empty[64]
         misc = o; o += 128;                              // [0] stages, [1 + r] cells of row r every view sees
         sH = o; o += V * 48;                             // homographies, rows padded to 4 floats
         ring = up(o, 128);
@@ -94,7 +98,6 @@ struct StagedSmem {
         ginfo = o; o += R * V * 16;                      // per (row, view): kind, first gtab row of its group, group's first texel row, real reloads
         vst = o; o += V * R * 32;                        // per (view, stage of the view): row mask, bytes, ops, kind, gtab row, first texel row, texel rows, row
         vcnt = o; o += up(V * 8, 16);                    // per view: stages, ops
-        soff = o; o += nst_max * 4;                      // ring offsets while the places are dealt
         scratch_end = o;
     }
 };
@@ -123,10 +126,11 @@ enum { ST_SPANS = 1, ST_BLOCKS = 2 };
 // Builds, for the tile at (i0, j0) of frame b: blend weights, the stage list with its row copies, ring places and
 // predecessor distances, every (row, view, cell)'s tap offsets inside its stage and every warp's per-stage word.
 template <int NW, bool WANT_ALL_SEEN>
-__device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSmem& L, unsigned char* sm, int ring_bytes, int cap, int i0, int j0, int b) {
+__device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSmem& L, unsigned char* sm, int cap, int i0, int j0, int b) {
     constexpr int CELLS = kStCells, GPW = 32 / CELLS, NT = NW * 32;
     constexpr unsigned CMASK = (1u << CELLS) - 1u;
     static_assert(NW == 4 || NW == 8 || NW == 16, "rows per tile");
+    static_assert(kStBack == 64, "barrier pair = stage & 63, parity = stage >> 6");
     const int V = p.V, GT = L.gt;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int gl = lane / CELLS, c = lane - gl * CELLS;
@@ -146,7 +150,6 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
     int4* ginfo = reinterpret_cast<int4*>(sm + L.ginfo);
     int* vst = reinterpret_cast<int*>(sm + L.vst);      // [(v * NW + k) * 8 + ...]
     int* vcnt = reinterpret_cast<int*>(sm + L.vcnt);    // [v * 2 + {stages, ops}]
-    int* soff = reinterpret_cast<int*>(sm + L.soff);
     constexpr int IMAX = 0x7fffffff, IMIN = (int)0x80000000;
 
     // ---- P0: homographies (geometry.py:60-63), scratch initialisation -------------------------------------------
@@ -373,7 +376,7 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
     }
     __syncthreads();
 
-    // ---- P6: static places in the ring and predecessor distances (warp 0); every warp's per-stage words ---------------
+    // ---- P6: every warp's per-stage words ---------------------------------------------------------------------------
     for (int s = lane; s < nst; s += 32) {
         const int w = sdesc[s].w;
         const int v = w & 0xff;
@@ -381,45 +384,66 @@ __device__ __forceinline__ void staged_build(const FwdParams& p, const StagedSme
         const bool mine = ((w >> (8 + r)) & 1) && (m & 0xffffu);
         wst[r * L.nst_max + s] = mine ? ((m & 0xffu) | (((m >> 16) & 0xffu) << 8) | ((unsigned)v << 24)) : 0u;
     }
-    if (warp == 0) {
-        if (lane == 0) {
-            int pos = 0;
-            for (int s = 0; s < nst; ++s) {
-                const int bts = (sdesc[s].x + 127) & ~127;
-                if (pos + bts > ring_bytes) pos = 0;      // wrap: a stage is contiguous
-                soff[s] = pos;
-                pos += bts;
-            }
-        }
-        __syncwarp();
-        for (int s = 0; s < nst; ++s) {
-            const int so = soff[s], sb = sdesc[s].x;
-            int dback = nst;                              // the same stage, one item earlier
-            if (sb > 0) {
-                for (int k0 = 1; k0 < nst && dback == nst; k0 += 32) {
-                    const int k = k0 + lane;
-                    bool hit = false;
-                    if (k < nst) {
-                        int q = s - k;
-                        if (q < 0) q += nst;
-                        const int qo = soff[q], qb = sdesc[q].x;
-                        hit = qb > 0 && qo < so + sb && so < qo + qb;
-                    }
-                    const unsigned hb = __ballot_sync(0xffffffffu, hit);
-                    if (hb) dback = k0 + __ffs(hb) - 1;
-                }
-            }
-            if (lane == 0) sdesc[s].y = (so >> 7) | (dback << 16);
-        }
-    }
     // the scratch arrays were written and read through the generic proxy; the TMA unit (async proxy) writes the ring next
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncthreads();
 }
 
+// ---- the copy schedule of one run (warp 0) ---------------------------------------------------------------------------
+// The PL = P * nst stages of P consecutive items get consecutive places in the ring (a stage is contiguous: one that does
+// not fit before the end starts again at offset 0), then every stage learns how many stages back its PREDECESSOR is: the
+// last stage before it whose bytes it overwrites, which every warp must have left before the copy may be issued.  The
+// schedule repeats with period PL (P = all items of the run when they fit the table: then there is no repetition at
+// all).  Looking back at most kStBack stages and never letting a predecessor be older than the one of the stage before
+// are both on the safe side: a later stage is waited for than strictly necessary.
+__device__ __forceinline__ void staged_schedule(const StagedSmem& L, unsigned char* sm, int nst, int PL, int ring_bytes, int lane) {
+    int2* sched = reinterpret_cast<int2*>(sm + L.sched);
+    const int4* sdesc = reinterpret_cast<const int4*>(sm + L.sdesc);
+    if (lane == 0) {
+        int pos = 0, s = 0;
+        for (int q = 0; q < PL; ++q) {
+            const int bts = sdesc[s].x;
+            const int al = (bts + 127) & ~127;
+            if (pos + al > ring_bytes) pos = 0;
+            sched[q] = make_int2(pos >> 7, bts);
+            pos += al;
+            if (++s == nst) s = 0;
+        }
+    }
+    __syncwarp();
+    const int kmax = min(PL, kStBack);
+    for (int q = lane; q < PL; q += 32) {
+        const int2 me = sched[q];
+        const int so = (me.x & 0xffff) << 7, sb = me.y;
+        int dback = kmax;
+        if (sb > 0) {
+            for (int k = 1; k < kmax; ++k) {
+                int q2 = q - k;
+                if (q2 < 0) q2 += PL;
+                const int2 o = sched[q2];
+                const int qo = (o.x & 0xffff) << 7;
+                if (o.y > 0 && qo < so + sb && so < qo + o.y) { dback = k; break; }
+            }
+        }
+        sched[q].x = (me.x & 0xffff) | (dback << 16);
+    }
+    __syncwarp();
+    if (lane == 0) {  // predecessors in non-decreasing order, also across the period boundary
+        int prev = sched[PL - 1].x >> 16;
+        for (int pass = 0; pass < 2; ++pass)
+            for (int q = 0; q < PL; ++q) {
+                const int x = sched[q].x;
+                int d = x >> 16;
+                if (d > prev + 1) { d = prev + 1; sched[q].x = (x & 0xffff) | (d << 16); }
+                prev = d;
+            }
+    }
+}
+
 // ---- the kernel ---------------------------------------------------------------------------------------------------
 // KMODE: KM_ACC = sum / mean (fusion.py:18-21), KM_MAX = max over views with the zeros of views that miss a cell
-// (fusion.py:22).  PROBE (timing aid, results are NOT the fusion): 1 = no TMA copies are issued.
+// (fusion.py:22).  PROBE (timing aids, results are NOT the fusion): 1 = no TMA copies are issued (instruction side alone),
+// 2 = copies but no blend (memory side alone).
 // ring_bytes: size of the stage ring; cap: largest stage (bytes); lag: a stage is armed `lag` stages after its
 // predecessor in the ring was walked (1 = as soon as possible: the arming warp then waits for the slowest warp).
 template <typename TIn, typename TOut, int NW, int MAXREG, int KMODE, int PROBE = 0>
@@ -443,7 +467,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
     const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_st);
     const uint32_t s_wts = sbase + L.wts + r * V * CELLS * 16, s_ent = sbase + L.ent + r * V * CELLS * 8;
     const uint32_t s_wst = sbase + L.wst + r * L.nst_max * 4, s_sdesc = sbase + L.sdesc, s_ops = sbase + L.ops;
-    const uint32_t s_full = sbase + L.bars, s_empty = s_full + L.nst_max * 8;
+    const uint32_t s_full = sbase + L.bars, s_empty = s_full + kStBack * 8;
     const uint32_t s_ring = sbase + L.ring;
     uint32_t lring = s_ring + lane * 16;
     asm volatile("" : "+r"(lring));
@@ -451,18 +475,12 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
     for (int b = b0; b < b1;) {
         if (b > b0) {
             __syncthreads();  // every warp is done with the previous run's tables and ring
-            for (int s = tid; s < 2 * L.nst_max; s += NT) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(s_full + s * 8) : "memory");
+            for (int s = tid; s < 2 * kStBack; s += NT) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(s_full + s * 8) : "memory");
             __syncthreads();
         }
-        for (int s = tid; s < L.nst_max; s += NT) { mbar_init(s_full + s * 8, 1); mbar_init(s_empty + s * 8, NW); }
+        for (int s = tid; s < kStBack; s += NT) { mbar_init(s_full + s * 8, 1); mbar_init(s_empty + s * 8, NW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        staged_build<NW, KMODE == KM_MAX>(p, L, smem_st, ring_bytes, cap, i0, j0, b);
-        if (dump) {  // development aid (BEVIPM_ST_DUMP): the tables of every tile, no phase B
-            unsigned char* dst = dump + ((size_t)blockIdx.z * gridDim.x + blockIdx.x) * (size_t)L.ring;
-            for (int z = tid * 4; z < L.ring; z += NT * 4) *reinterpret_cast<int*>(dst + z) = *reinterpret_cast<const int*>(smem_st + z);
-            return;
-        }
-
+        staged_build<NW, KMODE == KM_MAX>(p, L, smem_st, cap, i0, j0, b);
         // ---- the run of frames b .. e-1 shares these tables: same calibration, bit for bit (static cameras) ----------
         int e = b1;
         if (b + 1 < b1) {
@@ -491,18 +509,33 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
         b = e;
         const int nst = __shfl_sync(0xffffffffu, lds4i(sbase + L.misc), 0);
         const int total = n_items * nst;  // stages of this run
+        // the copy schedule: one period = as many whole items as the table holds (normally the whole run)
+        const int PL = nst > 0 ? max(1, min(n_items, kStSched / nst)) * nst : 0;
+        if (warp == 0 && nst > 0) staged_schedule(L, smem_st, nst, PL, ring_bytes, lane);
+        __syncthreads();
+        if (dump) {  // development aid (BEVIPM_ST_DUMP): the tables and the copy schedule of every tile, no phase B
+            unsigned char* dst = dump + ((size_t)blockIdx.z * gridDim.x + blockIdx.x) * (size_t)L.ring;
+            for (int z = tid * 4; z < L.ring; z += NT * 4) *reinterpret_cast<int*>(dst + z) = *reinterpret_cast<const int*>(smem_st + z);
+            return;
+        }
 
-        // arm stage ga = (item ia, stage sa): warp-uniform; one elected lane talks to the TMA unit
-        auto arm = [&](int ga, int sa, int ia) {
+        const uint32_t s_sched = sbase + L.sched;
+        if (PROBE == 1) {  // no copies: blend zeros instead of whatever the ring holds (NaNs would take the slow division)
+            for (int z = tid * 16; z < ring_bytes; z += NT * 16) *reinterpret_cast<uint4*>(smem_st + L.ring + z) = make_uint4(0u, 0u, 0u, 0u);
+            __syncthreads();
+        }
+
+        // arm stage ga = (item ia, stage sa), schedule entry qa: warp-uniform; one elected lane talks to the TMA unit
+        auto arm = [&](int ga, int qa) {
+            const int ia = ga / nst, sa = ga - ia * nst;
             const int4 sd = lds16i(s_sdesc + sa * 16);
-            const int dback = sd.y >> 16;
-            if (ga - dback >= 0) {  // the last stage that used these bytes: every warp must have left it
-                int ps = sa - dback, pit = ia;
-                if (ps < 0) { ps += nst; --pit; }
-                mbar_wait(s_empty + ps * 8, (uint32_t)pit & 1u);
-            }
+            const int2 sc = lds8i(s_sched + qa * 8);
+            const int pred = ga - (sc.x >> 16);
+            // the last stage that used these bytes: every warp must have left it.  (That stage is at most 64 back, so
+            // this also frees the mbarrier pair of stage ga - 64, which is the one stage ga uses.)
+            if (pred >= 0) mbar_wait(s_empty + (pred & (kStBack - 1)) * 8, (uint32_t)(pred >> 6) & 1u);
             if (elect_one()) {
-                const uint32_t bar = s_full + sa * 8, dst0 = s_ring + ((uint32_t)(sd.y & 0xffff) << 7);
+                const uint32_t bar = s_full + (ga & (kStBack - 1)) * 8, dst0 = s_ring + ((uint32_t)(sc.x & 0xffff) << 7);
                 mbar_expect_tx(bar, sd.x);
                 if (PROBE != 1) {
                     const int o0 = sd.z & 0xffff, n = sd.z >> 16;
@@ -519,14 +552,12 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
             }
             __syncwarp();
         };
-        // when stage ga is due: `lag` stages after its predecessor in the ring, at the latest when it is walked itself
-        auto due = [&](int ga, int sa) { return ga < total ? min(ga, ga - (lds4i(s_sdesc + sa * 16 + 4) >> 16) + lag) : 0x7fffffff; };
+        // when stage ga is due: `lag` stages after its predecessor in the ring was walked, at the latest when it is walked itself
+        auto due = [&](int ga, int qa) { return ga < total ? min(ga, ga - (lds4i(s_sched + qa * 8) >> 16) + lag) : 0x7fffffff; };
 
-        int ga = 0, sa = 0, ia = 0;   // next stage to arm: global index, stage, item
+        int ga = 0, qa = 0;           // next stage to arm: global index, schedule entry
         int at = nst > 0 ? due(0, 0) : 0x7fffffff;
-        int g = 0;                    // stage being walked (global index)
-        int duty = 0;                 // g % NW
-        int fi_c = 0, k_c = 0;
+        int g = 0, qg = 0;            // stage being walked: global index, schedule entry
         float2 cur[4][P];
 #pragma unroll
         for (int tap = 0; tap < 4; ++tap)
@@ -538,20 +569,19 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
             for (int c = 0; c < CELLS; ++c)
 #pragma unroll
                 for (int q = 0; q < P; ++q) acc[c][q] = (KMODE == KM_MAX) ? make_float2(-INFINITY, -INFINITY) : make_float2(0.0f, 0.0f);
-            const uint32_t par = (uint32_t)it & 1u;
 
             for (int s = 0; s < nst; ++s) {
                 while (at <= g) {  // every warp follows the schedule; the warp on duty issues
-                    if (duty == warp) arm(ga, sa, ia);
+                    if ((g & (NW - 1)) == warp) arm(ga, qa);
                     ++ga;
-                    if (++sa == nst) { sa = 0; ++ia; }
-                    at = due(ga, sa);
+                    if (++qa == PL) qa = 0;
+                    at = due(ga, qa);
                 }
                 const unsigned m = (unsigned)__shfl_sync(0xffffffffu, lds4i(s_wst + s * 4), 0);  // seen | reload << 8 | view << 24
-                mbar_wait(s_full + s * 8, par);  // the stage's bytes have landed
-                if (m) {
+                mbar_wait(s_full + (g & (kStBack - 1)) * 8, (uint32_t)(g >> 6) & 1u);  // the stage's bytes have landed
+                if (m && PROBE != 2) {
                     const int v = (int)(m >> 24);
-                    const uint32_t sb = lring + (((uint32_t)lds4i(s_sdesc + s * 16 + 4) & 0xffffu) << 7);
+                    const uint32_t sb = lring + (((uint32_t)lds4i(s_sched + qg * 8) & 0xffffu) << 7);
                     const uint32_t wv = s_wts + v * (CELLS * 16), ev = s_ent + v * (CELLS * 8);
                     float4 wn = lds16f(wv);
 #pragma unroll
@@ -594,14 +624,13 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_staged_kernel(const FwdParams p, i
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(s_empty + s * 8);  // this warp is done with the stage's bytes
+                if (lane == 0) mbar_arrive(s_empty + (g & (kStBack - 1)) * 8);  // this warp is done with the stage's bytes
                 ++g;
-                if (++duty == NW) duty = 0;
+                if (++qg == PL) qg = 0;
             }
 
             // ---- epilogue: mean division (IEEE quotient) and one 16-byte store per cell ---------------------------
-            const int k_this = k_c, fi_this = fi_c;
-            if (++k_c == chunks) { k_c = 0; ++fi_c; }
+            const int fi_this = it / chunks, k_this = it - fi_this * chunks;
             const bool lok = k_this * 32 + lane <= last_vec;
             if (i >= p.Hb) continue;
             if constexpr (KMODE == KM_MAX) {
