@@ -54,6 +54,10 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-concat", action="store_true", help="skip the informational per-view (concat) mode block")
     ap.add_argument("--e2e-steps", type=int, default=0, help="0 = min(steps, 20)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the informational blocks outside the timed region (sustained run, stock-torch GPU chain, batch-1 latency, view sharding)")
+    ap.add_argument("--measure-traffic", action="store_true",
+                    help="measure roofline.traffic live: re-run one launch of this workload under ncu (dram__bytes_read/write) and refresh profiles/traffic.json")
     ap.add_argument("--shard", default="frames", choices=["frames", "views"],
                     help="N>1: frames = every rank runs its own batch (weak scaling, no collective); "
                          "views = ranks split the cameras of ONE batch and all-reduce partial BEVs (strong scaling)")
@@ -123,15 +127,76 @@ class ClockSampler:
 
 
 def ncu_traffic(workload: str, variant: int):
-    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/traffic.json)."""
+    """(DRAM bytes per launch of the dominant kernel, where the number comes from): the committed ncu capture
+    (profiles/traffic.json) of the kernel variant that actually ran, else (None, reason)."""
     p = ROOT / "profiles" / "traffic.json"
     try:
         t = json.loads(p.read_text()).get(workload)
-        if t and int(t.get("variant", -1)) == int(variant):
-            return int(t["dram_bytes_per_launch"])
-    except Exception:
-        pass
-    return None
+        if t and int(t.get("kernel_variant", t.get("variant", -1))) == int(variant):
+            return int(t["dram_bytes_per_launch"]), f"committed ncu capture ({t.get('source', 'profiles/traffic.json')})"
+        if t:
+            return None, f"no capture of kernel variant {variant} (profiles/traffic.json holds variant {t.get('kernel_variant')})"
+    except Exception as e:
+        return None, f"profiles/traffic.json unreadable: {e!r}"
+    return None, "no capture of this workload in profiles/traffic.json"
+
+
+def measure_traffic_live(workload: str, variant: int, requested_variant: int = 0):
+    """One launch of this workload under `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` (a subprocess of this
+    script with the informational blocks off); the sum refreshes profiles/traffic.json.  Not a timing."""
+    import csv
+    import io
+    import shutil
+    if not shutil.which("ncu"):
+        return None, "ncu not on PATH"
+    cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:warp_fuse",
+           "-s", "3", "-c", "1", "--csv", sys.executable, str(ROOT / "bench.py"), "--workload", workload, "--variant", str(requested_variant),
+           "--steps", "1", "--warmup", "3", "--no-e2e", "--no-cpu", "--no-concat", "--no-extras"]
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
+        rows = [r for r in csv.reader(io.StringIO(out)) if len(r) > 5]
+        hdr = rows[0]
+        mi, vi, ui = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for r in rows[1:]:
+            if r[mi].startswith("dram__bytes_"):
+                tot += float(r[vi].replace(",", "")) * scale.get(r[ui], 1)
+        if tot <= 0:
+            return None, "ncu returned no dram__bytes rows"
+        p = ROOT / "profiles" / "traffic.json"
+        try:
+            t = json.loads(p.read_text())
+        except Exception:
+            t = {}
+        t[workload] = {"kernel_variant": int(variant), "dram_bytes_per_launch": int(tot), "source": "bench.py --measure-traffic (ncu, one launch)"}
+        p.write_text(json.dumps(t, indent=1))
+        return int(tot), "measured in this run (ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum, one launch)"
+    except Exception as e:
+        return None, f"live ncu measurement failed: {e!r}"
+
+
+def bind_to_gpu_numa(local: int):
+    """Pin this process (and the pinned host buffers it allocates next: first touch) to the NUMA node of its GPU's PCIe
+    root.  Round 1: all 8 ranks streamed from node 0 and the end-to-end path scaled 0.33 at N = 8."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{getattr(pr, 'pci_domain_id', 0):04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(Path(f"/sys/bus/pci/devices/{bdf}/numa_node").read_text().strip())
+        if node < 0:
+            return {"node": None, "note": f"{bdf}: no NUMA affinity reported"}
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return {"node": node, "note": "none of the node's CPUs are in this process's affinity mask"}
+        os.sched_setaffinity(0, allowed)
+        return {"node": node, "cpus": len(allowed), "pci": bdf}
+    except Exception as e:   # sysfs layout / permissions differ between boxes: informational only
+        return {"node": None, "note": repr(e)[:120]}
 
 
 def measured_peak():
@@ -219,6 +284,214 @@ def run_reference(args, wl):
     except Exception as e:  # informational only
         line["torch_cpu_chain"] = {"error": repr(e)}
     print(json.dumps(line), flush=True)
+
+
+
+# ---------------------------------------------------------------------------------------------
+# informational blocks, all OUTSIDE the timed region of the headline metric
+def sustained_block(step, frames, bytes_per_launch, peak, launches: int = 200):
+    """>= 200 back-to-back launches: the sustained figure beside the (short) timed region's burst figure."""
+    import torch
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(launches):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / launches
+    gbs = bytes_per_launch / (ms * 1e-3) / 1e9
+    return {"launches": launches, "ms_per_step": ms, "frames_per_s": frames / (ms * 1e-3), "achieved_gbs": gbs, "frac": gbs / peak}
+
+
+def torch_gpu_chain_block(wl, dev, ours_ms_per_frame: float):
+    """The reference's op chain on ATen's CUDA kernels on this very GPU (oracle/torch_chain.py: aten::mm, the pointwise
+    chain, grid_sampler_2d, mean; default 'highest' fp32 matmul precision; ~175 launches per frame): the stock-torch arm
+    of BASELINE.md 4.4 / geometry.py:142-162, one frame of the workload, features up-cast to fp32 as the reference
+    requires.  Also the distance between that result and ours on the same frame."""
+    import torch
+    from bevipm import _lib, ops, rig
+    from oracle import torch_chain
+    V, C = wl.views, wl.channels
+    K, Rt = rig.look_at_rig(V, 0)
+    xs, ys = rig.ground_axes(*wl.bev_hw, wl.bounds)
+    g = torch.Generator(device=dev).manual_seed(1)
+    f = torch.randn((1, V, *wl.feat_hw, C), device=dev, generator=g)
+    if wl.dtype == "bf16":
+        f = f.bfloat16().float()
+    f = f.permute(0, 1, 4, 2, 3)                                   # logical NCHW, channels-last memory (ours)
+    f_nchw = f.contiguous()                                        # what the reference's encoder hands over
+    Kd, Rd = K[None].to(dev), Rt[None].to(dev)
+    with torch.no_grad():
+        ref = torch_chain.warp_fuse(f_nchw, Kd, Rd, xs, ys, wl.img_size, wl.fusion)
+        torch.cuda.synchronize(dev)
+        times = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ref = torch_chain.warp_fuse(f_nchw, Kd, Rd, xs, ys, wl.img_size, wl.fusion)
+            torch.cuda.synchronize(dev)
+            times.append(time.perf_counter() - t0)
+    ours = ops.warp_fuse(f, Kd.contiguous(), Rd[:, :, :3, :].contiguous(), xs.to(dev), ys.to(dev), wl.img_size[0], wl.img_size[1],
+                         _lib.MODES[wl.fusion], False, 0)
+    diff = (ours - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    per_frame = min(times)
+    del ref, ours, f, f_nchw
+    torch.cuda.empty_cache()
+    return {"frames_per_s": 1.0 / per_frame, "ms_per_frame": per_frame * 1e3, "repeats": 3, "timing": "wall clock around one frame, synchronised (best of 3)",
+            "sample": f"1 frame of {wl.name}: {V} views x {C} ch fp32 NCHW, {wl.fusion}",
+            "ours_ms_per_frame": ours_ms_per_frame, "speedup_of_ours": per_frame * 1e3 / ours_ms_per_frame,
+            "max_abs_diff_vs_ours": diff, "max_normalised_diff_vs_ours": diff / scale if scale else None}
+
+
+def batch1_latency_block(dev):
+    """BASELINE configs[0] (c1: one frame, 7 x 512 ch fp32) as a latency path: the kernel alone, module.forward as a user
+    calls it (Python -> torch custom op -> ctypes -> C ABI -> launch), and the same forward replayed from a CUDA graph."""
+    import torch
+    from bevipm import _lib, modules, ops, rig
+    wl = rig.WORKLOADS["c1"]
+    V, C = wl.views, wl.channels
+    K, Rt = rig.look_at_rig(V, 0)
+    Kd = K[None].contiguous().to(dev)
+    Rd = Rt[None].contiguous().to(dev)
+    R34 = Rd[:, :, :3, :].contiguous()
+    xs, ys = rig.ground_axes(*wl.bev_hw, wl.bounds)
+    xd, yd = xs.to(dev), ys.to(dev)
+    g = torch.Generator(device=dev).manual_seed(2)
+    bufs = [torch.randn((1, V, *wl.feat_hw, C), device=dev, generator=g).permute(0, 1, 4, 2, 3) for _ in range(2)]
+    mod = modules.FusedIPM(wl.bev_hw[0], wl.bev_hw[1], wl.bounds, fusion=wl.fusion, layout="keep").to(dev)
+    n = 200
+
+    def timed(fn):
+        for _ in range(5):
+            fn(0)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n, (time.perf_counter() - t0) * 1e3 / n
+
+    k_dev, k_wall = timed(lambda i: ops.warp_fuse(bufs[i & 1], Kd, R34, xd, yd, wl.img_size[0], wl.img_size[1], _lib.MODES[wl.fusion], False, 0))
+    with torch.no_grad():
+        m_dev, m_wall = timed(lambda i: mod(bufs[i & 1], Kd, Rd, img_size=wl.img_size))
+    res = {"workload": "c1: 1 frame x 7 views x 512 ch fp32 135x240 -> 120x360, mean", "calls": n,
+           "op_call_ms": {"device": k_dev, "wall": k_wall}, "module_forward_ms": {"device": m_dev, "wall": m_wall}}
+    try:
+        static_in = bufs[0].clone()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(3):
+                mod(static_in, Kd, Rd, img_size=wl.img_size)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(graph):
+            static_out = mod(static_in, Kd, Rd, img_size=wl.img_size)
+        g_dev, g_wall = timed(lambda i: graph.replay())
+        want = mod(static_in, Kd, Rd, img_size=wl.img_size)
+        res["cuda_graph_replay_ms"] = {"device": g_dev, "wall": g_wall, "matches_eager": bool(torch.equal(static_out, want))}
+    except Exception as e:   # informational
+        res["cuda_graph_replay_ms"] = {"error": repr(e)[:200]}
+    return res
+
+
+def view_sharded_block(dev, world: int, rank: int, steps: int = 30):
+    """BASELINE configs[2]: c3 (7 views x 128 ch fp32 270x480 -> 480x1440 BEV), the cameras of ONE frame split over the
+    ranks.  compute_only = every rank warps its cameras into a partial sum, no exchange; then the three exchange forms of
+    bevipm/sharding.py.  Times are device times (CUDA events), max over ranks; bytes are what one rank sends over NVLink."""
+    import torch
+    import torch.distributed as dist
+    from bevipm import _lib, ops, rig, sharding
+    wl = rig.WORKLOADS["c3"]
+    V, C = wl.views, wl.channels
+    Hb, Wb = wl.bev_hw
+    K, Rt = rig.look_at_rig(V, 0)
+    xs, ys = rig.ground_axes(Hb, Wb, wl.bounds)
+    xd, yd = xs.to(dev), ys.to(dev)
+    ids = sharding.view_assignment(V, world)[rank]
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    nv = max(len(ids), 1)
+    f_r = torch.randn((1, nv, *wl.feat_hw, C), device=dev, generator=g).permute(0, 1, 4, 2, 3)
+    sel = ids if ids else [0]
+    K_r = K[sel][None].contiguous().to(dev)
+    R_r = Rt[sel, :3, :][None].contiguous().to(dev)
+    img = wl.img_size
+    bev_bytes = Hb * Wb * C * 4
+
+    def partial():
+        if ids:
+            return ops.warp_fuse(f_r, K_r, R_r, xd, yd, img[0], img[1], _lib.SUM, False, 0)
+        return torch.zeros((1, Hb, Wb, C), device=dev).permute(0, 3, 1, 2)
+
+    def timed(fn, fin=None):
+        for _ in range(3):
+            fn()
+        if fin:
+            fin()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        if fin:
+            fin()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    out = {"workload": "c3: 1 frame x 7 views x 128 ch fp32 270x480 -> 480x1440 BEV, mean; cameras split "
+                       f"{[len(a) for a in sharding.view_assignment(V, world)]} over {world} ranks",
+           "partial_bev_bytes": bev_bytes, "steps": steps}
+    ms = timed(partial)
+    out["compute_only"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "note": "partial sums only, no exchange (not a result)"}
+    # (1) all-reduce: every rank ends with the whole BEV
+    ar = sharding.ViewShardedFusion(V, wl.fusion)
+    ms = timed(lambda: ar(lambda v: partial(), (1, C, Hb, Wb), dev))
+    sent = 2 * (world - 1) / world * bev_bytes
+    out["allreduce"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "nvlink_bytes_per_rank": int(sent), "nvlink_gbs_per_rank": sent / ms / 1e6,
+                        "result": "whole BEV on every rank", "collective": "ncclAllReduce(sum, fp32), in line"}
+    # (2) reduce-scatter on a side stream: warp of frame t+1 overlaps the exchange of frame t; rank keeps Hb/N rows
+    rs = sharding.ReduceScatterFusion(V, (Hb, Wb), C, wl.fusion, device=dev)
+    pending = []
+
+    def rs_step():
+        pending.append(rs.submit(partial()))
+        if len(pending) > 2:
+            rs.wait(pending.pop(0))
+
+    def rs_drain():
+        while pending:
+            rs.wait(pending.pop(0))
+
+    ms = timed(rs_step, rs_drain)
+    sent = (world - 1) / world * bev_bytes
+    out["reduce_scatter_overlapped"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "nvlink_bytes_per_rank": int(sent),
+                                        "nvlink_gbs_per_rank": sent / ms / 1e6, "result": f"{sharding.slab_rows(Hb, world)} BEV rows per rank",
+                                        "collective": "ncclReduceScatter(sum, fp32) on a second stream, two frames in flight"}
+    # (3) fused: the warp kernel adds its partial into the owners' slabs through peer memory
+    try:
+        ps = sharding.PeerSlabFusion(V, (Hb, Wb), C, frames=1, mode=wl.fusion, device=dev)
+        ms = timed(lambda: ps.run(f_r if ids else None, K_r, R_r, xd, yd, img))
+        sent = ps.bytes_over_nvlink_per_call()
+        t = torch.tensor([float(sent)], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["peer_slab_fused"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "nvlink_bytes_per_rank": int(t.item()),
+                                  "nvlink_gbs_per_rank": float(t.item()) / ms / 1e6, "result": f"{sharding.slab_rows(Hb, world)} BEV rows per rank",
+                                  "collective": "none: red.global.add.v4.f32 from the warp kernel into peer slabs (symmetric memory), "
+                                                "one cross-rank barrier per frame"}
+    except Exception as e:
+        out["peer_slab_fused"] = {"error": repr(e)[:300]}
+    out["nvlink_reference_gbs"] = {"peer_copy_per_direction": 770, "allreduce_bus_8_ranks": 725, "source": "B200_PROFILING.md"}
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -354,7 +627,11 @@ def run_ours(args, wl):
 
     # ---- end to end through the host-buffer entry of the C ABI ---------------------------------
     e2e = None
+    numa = None
     if not args.no_e2e and not views_mode:
+        # NUMA-local pinned buffers: bind to the CPUs of this GPU's PCIe root before the first touch (restored below)
+        mask0 = os.sched_getaffinity(0)
+        numa = bind_to_gpu_numa(local)
         hf = torch.empty((B, V, *wl.feat_hw, C), dtype=tdt, pin_memory=True)
         hf.copy_(feats.permute(0, 1, 3, 4, 2))
         ho = torch.empty((B, *wl.bev_hw, C), dtype=torch.bfloat16 if out_bf16 else torch.float32, pin_memory=True)
@@ -380,13 +657,48 @@ def run_ours(args, wl):
                "d2h_bytes_per_step": ho.numel() * ho.element_size(), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
                "api": "bevipm_warp_fuse_host (pinned host in -> H2D of the source-row spans any BEV cell samples -> fused kernel -> "
                       "D2H -> pinned host out, double-buffered per frame)", "matches_device_path": ok}
+        e2e["numa"] = numa
         _lib.load().bevipm_host_release()
+        del hf, ho
+        os.sched_setaffinity(0, mask0)
         barrier()
     clocks = sampler.stop() if sampler else None
+
+    # ---- informational blocks (outside every timed region) -----------------------------------------------------------
+    extras = {}
+    if not args.no_extras and not views_mode:
+        peak0, _ = measured_peak()
+        if world == 1:
+            try:
+                extras["sustained"] = sustained_block(step, B, bytes_per_launch, peak0)
+            except Exception as e:
+                extras["sustained"] = {"error": repr(e)[:200]}
+            try:
+                extras["torch_gpu_chain"] = torch_gpu_chain_block(wl, dev, ms_per_step / B)
+            except Exception as e:
+                extras["torch_gpu_chain"] = {"error": repr(e)[:200]}
+            try:
+                extras["batch1_latency"] = batch1_latency_block(dev)
+            except Exception as e:
+                extras["batch1_latency"] = {"error": repr(e)[:200]}
+        else:
+            try:
+                del feats, out
+                torch.cuda.empty_cache()
+                extras["view_sharded"] = view_sharded_block(dev, world, rank)
+            except Exception as e:
+                extras["view_sharded"] = {"error": repr(e)[:300]}
 
     if rank == 0:
         peak, peak_src = measured_peak()
         achieved = bytes_per_launch / (ms_per_step * 1e-3) / 1e9
+        if args.measure_traffic and world == 1:
+            traffic, traffic_src = measure_traffic_live(wl.name, kernel_variant, args.variant)
+            if traffic is None:
+                t2, s2 = ncu_traffic(wl.name, kernel_variant)
+                traffic, traffic_src = t2, f"{traffic_src}; {s2}"
+        else:
+            traffic, traffic_src = ncu_traffic(wl.name, kernel_variant)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if views_mode else "weak",
@@ -400,11 +712,18 @@ def run_ours(args, wl):
                 "variant": args.variant, "arithmetic": "fp32 (bit-exact op chain of the reference), storage as named"}),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(wl.name, args.variant), "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                          "algorithmic_bytes_per_frame": alg["b_alg"], "b_full_per_frame": alg["b_full"],
                          "frac_of_nominal_8TBs": achieved / 8000.0, "kernel": _lib.variant_name(kernel_variant)},
             "clocks": clocks,
         }
+        if "sustained" in extras and "frac" in extras["sustained"]:
+            line["roofline"]["sustained_frac"] = extras["sustained"]["frac"]
+            line["roofline"]["sustained_ms_per_step"] = extras["sustained"]["ms_per_step"]
+            line["roofline"]["sustained_launches"] = extras["sustained"]["launches"]
+        for k in ("torch_gpu_chain", "batch1_latency", "view_sharded"):
+            if k in extras:
+                line[k] = extras[k]
         if e2e:
             line["e2e"] = e2e
         if concat:

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define BEVIPM_VERSION 100 /* 0.1.0 */
+#define BEVIPM_VERSION 200 /* 0.2.0 */
 
 enum bevipm_status {
     BEVIPM_OK = 0,
@@ -114,6 +114,36 @@ int bevipm_nchw_to_nhwc(const void *src, void *dst, int32_t N, int32_t C, int32_
  * needs this; it exists so the stand-alone SimpleFusion module also runs on our kernels.) */
 int bevipm_fuse_views(const void *in, void *out, int64_t B, int32_t V, int64_t inner, int32_t mode,
                       int32_t in_dtype, int32_t out_dtype, void *stream);
+
+/* Backward of bevipm_fuse_views (autograd of fusion.py:17-22): grad_in [B,V,inner] f32 from grad_out [B,inner] f32 and, for
+ * MAX, the forward input `in` [B,V,inner] (in_dtype): the gradient goes to the first view holding the maximum, as torch.max
+ * does.  `in` may be null for SUM / MEAN. */
+int bevipm_fuse_views_bwd(const void *in, const float *grad_out, float *grad_in, int64_t B, int32_t V, int64_t inner,
+                          int32_t mode, int32_t in_dtype, void *stream);
+
+/*
+ * Validity-mask counts (north star): count [B,Hb,Wb] int32 = number of views that see each BEV cell, i.e. whose sample
+ * position has at least one bilinear tap inside the feature map -- the cells where geometry.py:161 reads anything but
+ * zero padding.  Uses d's extents, img size and flags; strides and dtypes are ignored.  The reference has no such output
+ * (its mean divides by V, fusion.py:20-21): an extension, off unless asked for, computed by its own small launch.
+ */
+int bevipm_valid_count(const bevipm_desc *d, const float *K, const float *Rt34, const float *xs, const float *ys,
+                       int32_t *count, void *stream);
+
+/* Opt-in "mean over the views that see the cell": divides a SUM-mode f32 result `bev` (strides d->os_*) in place by
+ * max(count, 1), IEEE division.  NOT the reference's mean (that is BEVIPM_MEAN: / V). */
+int bevipm_divide_by_count(const bevipm_desc *d, float *bev, const int32_t *count, void *stream);
+
+/*
+ * View sharding over peer memory (BASELINE configs[2]): the fused warp of THIS rank's cameras (feats / K /
+ * Rt34 hold only them: d->V = the rank's view count) adds its partial SUM into fp32 BEV row slabs owned by the ranks:
+ * BEV rows [q*slab_rows, (q+1)*slab_rows) go to slabs[q] (q < nslabs <= 16), each a buffer [B, slab_rows, Wb, C] with element
+ * strides d->os_b / os_y / os_x / os_c == 1 -- the rank's own memory or a peer's, mapped over NVLink (CUDA IPC, symmetric
+ * memory).  16-byte red.global.add: the partial never lands in this rank's HBM.  Callers zero the slabs and barrier
+ * across ranks before and after (bevipm/sharding.py: PeerSlabFusion).  d->mode must be BEVIPM_SUM, out_dtype f32.
+ */
+int bevipm_warp_fuse_red(const bevipm_desc *d, const void *feats, const float *K, const float *Rt34, const float *xs,
+                         const float *ys, void *const *slabs, int32_t nslabs, int32_t slab_rows, void *stream);
 
 /*
  * Phase-2 follow-on: multi-view, multi-head deformable-attention sampling (the slot the reference's

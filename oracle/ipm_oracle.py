@@ -166,3 +166,24 @@ def warp_fuse_bwd(gout, K, Rt, xs, ys, feat_shape, img_size, mode="mean"):
 
 def num_threads() -> int:
     return int(lib().ipm_oracle_num_threads())
+
+
+def valid_count(K, Rt, xs, ys, feat_hw, img_size) -> np.ndarray:
+    """count [B,Hb,Wb] int32: views whose sample position has at least one bilinear tap inside the feature map, i.e. the
+    cells where grid_sample (geometry.py:161: zeros padding, align_corners=False) reads anything but padding.  The
+    reference itself has no such output (its mean divides by V, fusion.py:20-21): the restatement of the north star's
+    "validity-mask counts", from the same coordinates as the warp."""
+    ix, iy = coords(K, Rt, xs, ys, feat_hw, img_size)
+    Hf, Wf = feat_hw
+    fin = np.isfinite(ix) & np.isfinite(iy)
+    x0 = np.floor(np.where(fin, ix, -5.0))
+    y0 = np.floor(np.where(fin, iy, -5.0))
+    seen = fin & (x0 >= -1) & (x0 <= Wf - 1) & (y0 >= -1) & (y0 <= Hf - 1)
+    return seen.sum(axis=1).astype(np.int32)
+
+
+def warp_fuse_mean_valid(feats, K, Rt, xs, ys, img_size):
+    """Opt-in extension: the sequential fp32 sum over views (fusion.py:18) divided by max(valid_count, 1) (IEEE fp32)."""
+    s = warp_fuse(feats, K, Rt, xs, ys, img_size, "sum")
+    cnt = valid_count(K, Rt, xs, ys, feats.shape[-2:], img_size)
+    return (s / np.maximum(cnt, 1).astype(np.float32)[:, None]).astype(np.float32), cnt

@@ -7,7 +7,9 @@ align_corners=False), aten::sum/mean/amax over the view axis -- so that
 
   * tests can cross-check the C oracle against ATen on any host (tests/test_oracle.py), and
   * `bench.py --impl reference` can report, next to the multi-threaded C port, what the
-    reference's own library calls cost on the box's CPU (informational key `torch_cpu_chain`).
+    reference's own library calls cost on the box's CPU (informational key `torch_cpu_chain`), and
+  * `bench.py` can time the same chain on ATen's CUDA kernels on the very B200 our kernel runs on (informational key
+    `torch_gpu_chain`: the stock-torch arm of BASELINE.md 4.4, ~175 launches per frame).
 
 It is never imported by the product package.
 """
@@ -25,13 +27,16 @@ def ground_homography(K: torch.Tensor, Rt: torch.Tensor) -> torch.Tensor:
 
 def warp_views(feats: torch.Tensor, K: torch.Tensor, Rt: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
                img_size) -> torch.Tensor:
-    """feats [B,V,C,Hf,Wf] fp32 CPU -> per-view BEV maps [B,V,C,Hb,Wb] (one grid_sample per view)."""
+    """feats [B,V,C,Hf,Wf] fp32 -> per-view BEV maps [B,V,C,Hb,Wb] (one grid_sample per view), on the device of `feats`
+    (CPU = the reference's path in this image; CUDA = the same chain on ATen's CUDA kernels, the stock-torch arm)."""
     B, V, C, Hf, Wf = feats.shape
     Hb, Wb = ys.numel(), xs.numel()
     img_h, img_w = img_size
+    dev = feats.device
+    K, Rt, xs, ys = K.to(dev), Rt.to(dev), xs.to(dev), ys.to(dev)
     yy, xx = torch.meshgrid(ys, xs, indexing="ij")
     pts = torch.stack([xx, yy, torch.ones_like(xx)], dim=-1).reshape(-1, 3).T      # [3, Hb*Wb]
-    out = torch.zeros(B, V, C, Hb, Wb)
+    out = torch.zeros(B, V, C, Hb, Wb, device=dev)
     for b in range(B):
         for v in range(V):
             uvw = ground_homography(K[b, v], Rt[b, v]) @ pts

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/bevipm.h but not exported"
     assert set(names) == set(_lib.EXPORTS)
-    assert L.bevipm_version() == 100
+    assert L.bevipm_version() == 200
 
 
 def test_desc_layout_matches_header():
@@ -163,3 +163,45 @@ def test_torch_chain_agrees_with_c_oracle():
         a = torch_chain.warp_fuse(f, Kb, Rb, xs, ys, rig.WILDTRACK_IMG_SIZE, mode).numpy()
         b = orc.warp_fuse(f.numpy(), Kb.numpy(), Rb.numpy(), xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, mode)
         assert np.array_equal(a, b), mode
+
+
+def test_round2_entry_points_check_their_arguments():
+    from bevipm import _lib
+    L = _lib.load()
+    d = _lib.Desc()
+    d.B = d.V = d.C = d.Hf = d.Wf = d.Hb = d.Wb = d.img_h = d.img_w = 4
+    d.mode = _lib.SUM
+    assert L.bevipm_valid_count(ctypes.byref(d), None, None, None, None, None, None) == -1
+    assert L.bevipm_divide_by_count(ctypes.byref(d), None, None, None) == -1
+    assert L.bevipm_fuse_views_bwd(None, None, None, 1, 2, 8, 0, 0, None) == -1
+    assert L.bevipm_warp_fuse_red(ctypes.byref(d), None, None, None, None, None, None, 2, 2, None) == -1
+    d.mode = _lib.MEAN   # the peer-memory form adds partial sums only
+    dummy = ctypes.c_void_p(16)
+    arr = (ctypes.c_void_p * 2)(16, 32)
+    assert L.bevipm_warp_fuse_red(ctypes.byref(d), dummy, ctypes.cast(dummy, ctypes.c_void_p), dummy, dummy, dummy, arr, 2, 2, None) == -2
+
+
+def test_kornia_decision_mirrors_the_reference():
+    """geometry.py:5-9 + :124: the kornia branch runs iff warp_impl == 'kornia' AND kornia imports.  kornia is not installed
+    in this image, so warp_impl='kornia' (what BEVNet passes, model_wrapper.py:42) resolves to the grid_sample geometry."""
+    import bevipm
+    from bevipm import modules
+    try:
+        import kornia  # noqa: F401
+        have = True
+    except Exception:
+        have = False
+    g = bevipm.GeometryTransformer(8, 8, (-1.0, 1.0, -1.0, 1.0), "kornia")
+    assert g.emulate_kornia == have
+    assert bevipm.GeometryTransformer(8, 8, (-1.0, 1.0, -1.0, 1.0), "grid_sample", emulate_kornia=True).emulate_kornia is False
+    with pytest.warns(UserWarning):
+        modules._KORNIA_NOTE = False
+        assert bevipm.FusedIPM(8, 8, (-1.0, 1.0, -1.0, 1.0), warp_impl="kornia", emulate_kornia=True).emulate_kornia is True
+    # singular feature->BEV matrices are found per view (geometry.py:134-136): a K with a zero focal length
+    K = torch.eye(3)[None, None].repeat(1, 2, 1, 1)
+    K[0, :, 0, 0] = K[0, :, 1, 1] = 1000.0
+    K[0, 1, 0, 0] = 0.0
+    Rt = torch.eye(4)[None, None, :3].repeat(1, 2, 1, 1)
+    Rt[..., 2, 3] = 5.0
+    sing = g._kornia_singular(K, Rt, (20, 30), (1080, 1920))
+    assert sing.tolist() == [[False, True]]

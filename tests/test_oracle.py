@@ -135,3 +135,25 @@ def test_oracle_vs_live_reference_full_spatial_size(shape):
     out = orc.warp_fuse(feats.numpy(), K.numpy(), Rt.numpy(), xs.numpy(), ys.numpy(),
                         rig.WILDTRACK_IMG_SIZE, "mean")
     assert np.array_equal(out, ref)
+
+
+@pytest.mark.parametrize("case", ["rig_small", "seven_views_3x4", "degenerate", "w_guard"])
+def test_valid_count_restatement_agrees_with_the_reference_per_view_maps(golden, case):
+    """The validity-count restatement (oracle.valid_count) against the REFERENCE's own per-view maps (golden out_none, made
+    by the imported reference module): a view counts for a cell iff the reference's map can be non-zero there, i.e. iff some
+    bilinear tap lies inside the feature map.  With random features a seen cell is non-zero in some channel."""
+    z = golden(case)
+    feats = z["feats"]
+    B, V = feats.shape[:2]
+    K = np.ascontiguousarray(np.broadcast_to(z["K"], (B, V) + z["K"].shape[-2:]))
+    Rt = np.ascontiguousarray(np.broadcast_to(z["Rt"], (B, V) + z["Rt"].shape[-2:]))
+    cnt = orc.valid_count(K, Rt, z["xs"], z["ys"], feats.shape[-2:], tuple(z["img_size"]))
+    nonzero_views = (z["out_none"] != 0).any(axis=2).sum(axis=1)           # [B,Hb,Wb] from the reference's output
+    assert cnt.shape == nonzero_views.shape
+    assert (cnt >= nonzero_views).all()                                    # an unseen view is exactly zero in the reference
+    assert (cnt == nonzero_views).mean() > 0.995                           # (a seen cell can still blend to 0: weight 0 taps)
+    mv, c2 = orc.warp_fuse_mean_valid(feats, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]))
+    s = orc.warp_fuse(feats, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]), "sum")
+    full = (c2 == V)[:, None].repeat(feats.shape[2], axis=1)
+    assert np.array_equal(mv[full], orc.warp_fuse(feats, K, Rt, z["xs"], z["ys"], tuple(z["img_size"]), "mean")[full])
+    assert np.array_equal(mv[~full & (np.broadcast_to(c2[:, None], s.shape) <= 1)], s[~full & (np.broadcast_to(c2[:, None], s.shape) <= 1)])

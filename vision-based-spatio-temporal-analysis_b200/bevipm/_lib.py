@@ -30,6 +30,7 @@ EXPORTS = (
     "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
     "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant", "bevipm_host_last_h2d_bytes",
+    "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -62,12 +63,16 @@ def load() -> ctypes.CDLL:
                                       ctypes.c_int32, vp]
     L.bevipm_fuse_views.argtypes = [vp, vp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32,
                                     ctypes.c_int32, ctypes.c_int32, vp]
+    L.bevipm_fuse_views_bwd.argtypes = [vp, fp, fp, ctypes.c_int64, ctypes.c_int32, ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, vp]
+    L.bevipm_valid_count.argtypes = [dp, fp, fp, fp, fp, vp, vp]
+    L.bevipm_divide_by_count.argtypes = [dp, vp, vp, vp]
+    L.bevipm_warp_fuse_red.argtypes = [dp, vp, fp, fp, fp, fp, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, vp]
     L.bevipm_warp_fuse_host.argtypes = [dp, vp, fp, fp, fp, fp, vp]
     L.bevipm_host_release.restype = None
     L.bevipm_deform_attn_fwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, vp]
     L.bevipm_deform_attn_fwd.restype = ctypes.c_int
     for name in ("bevipm_warp_fuse_fwd", "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc",
-                 "bevipm_fuse_views", "bevipm_warp_fuse_host"):
+                 "bevipm_fuse_views", "bevipm_warp_fuse_host", "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L
@@ -93,6 +98,8 @@ def variant_name(v: int) -> str:
         return f"warp_fuse_list_kernel (variant {v})"
     if 30 <= v <= 41:
         return f"warp_fuse_run_kernel (variant {v})"
-    if 50 <= v <= 52:
+    if v == 60:
+        return "warp_fuse_run_kernel<KM_RED> (partial sums added into peer slabs)"
+    if 50 <= v <= 53:
         return f"warp_fuse_staged_kernel (TMA-staged tiles, variant {v})"
     return f"variant {v}"

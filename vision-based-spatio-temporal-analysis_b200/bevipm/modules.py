@@ -77,6 +77,32 @@ def pack_calibration(intrinsics, extrinsics, B: int, V: int, device) -> Tuple[to
     return K, Rt
 
 
+_KORNIA_NOTE = False
+
+
+def _resolve_kornia(warp_impl: str, emulate_kornia) -> bool:
+    """The reference takes its kornia branch iff warp_impl == 'kornia' AND kornia imports (geometry.py:5-9, :124); BEVNet asks
+    for 'kornia' (model_wrapper.py:42).  emulate_kornia=None mirrors that decision: the kornia-compatible sample positions are
+    used exactly when `import kornia` works in this environment.  True / False force either geometry."""
+    global _KORNIA_NOTE
+    if warp_impl != "kornia":
+        return False
+    if emulate_kornia is None:
+        try:
+            import kornia  # noqa: F401
+            emulate_kornia = True
+        except Exception:
+            emulate_kornia = False
+    if emulate_kornia and not _KORNIA_NOTE:
+        _KORNIA_NOTE = True
+        import warnings
+        warnings.warn("bevipm: warp_impl='kornia' with kornia importable: using the kornia-compatible sample positions "
+                      "(BEV pixel at the cell corner, source pixel p read at p*size/(size-1) - 0.5).  This mode restates kornia's "
+                      "published warp_perspective and is NOT pinned against a kornia build; pass emulate_kornia=False for the "
+                      "reference's grid_sample geometry.", stacklevel=3)
+    return bool(emulate_kornia)
+
+
 class _IPMBase(nn.Module):
     def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple):
         super().__init__()
@@ -127,6 +153,10 @@ class _IPMBase(nn.Module):
         K, Rt = pack_calibration(intrinsics, extrinsics, B, V, feats.device)
         xs, ys = self._corner_axes(feats.device) if kornia_geometry else self._ground_axes(feats.device)
         if kornia_geometry:
+            # geometry.py:134-136: a view whose feature->BEV matrix M is singular takes the grid_sample geometry instead
+            sing = self._kornia_singular(K, Rt, feats.shape[-2:], img_size)
+            if bool(sing.any()):   # (one small read-back, only in the kornia-compatible mode)
+                return self._run_mixed(feats, K, Rt, sing, img_size, mode, out_bf16, variant, layout)
             mode = mode | (_lib.FLAG_KORNIA_GEOMETRY << 8)
         if layout == "channels_last" or (layout == "auto" and feats.shape[2] % (4 if feats.dtype == torch.float32 else 8) == 0):
             feats = ops.to_channels_last5(feats)
@@ -134,19 +164,54 @@ class _IPMBase(nn.Module):
         return ops.warp_fuse(feats, K, Rt, xs, ys, int(H_img), int(W_img), mode, out_bf16, variant)
 
 
+    def _kornia_singular(self, K, Rt34, feat_hw, img_size) -> torch.Tensor:
+        """bool [B,V]: |det(M)| < 1e-8 or not finite for M = A_w2bev @ H_img2world @ S_feat2img (geometry.py:125-134)."""
+        Hf, Wf = feat_hw
+        H_img, W_img = img_size
+        G = torch.stack([Rt34[..., 0], Rt34[..., 1], Rt34[..., 3]], dim=-1)
+        H = K @ G
+        det = torch.linalg.det(H)
+        bad = ~torch.isfinite(det) | (det.abs() < 1e-8)
+        Hinv = torch.where(bad[..., None, None], torch.linalg.pinv(H), torch.linalg.inv(torch.where(bad[..., None, None], torch.eye(3, device=H.device), H)))
+        S = torch.tensor([[W_img / float(Wf), 0.0, 0.0], [0.0, H_img / float(Hf), 0.0], [0.0, 0.0, 1.0]], device=H.device)
+        min_x, _, min_y, _ = self.bounds
+        A = torch.tensor([[1.0 / self.res_x, 0.0, -min_x / self.res_x], [0.0, 1.0 / self.res_y, -min_y / self.res_y], [0.0, 0.0, 1.0]],
+                         device=H.device)
+        detM = torch.linalg.det(A @ Hinv @ S)
+        return ~torch.isfinite(detM) | (detM.abs() < 1e-8)
+
+    def _run_mixed(self, feats, K, Rt, sing, img_size, mode, out_bf16, variant, layout):
+        """Kornia-compatible geometry for the regular views, grid_sample geometry for the singular ones (rare): two per-view
+        launches, a select, and the sequential view reduction of fusion.py:17-22 on our kernel."""
+        if layout == "channels_last" or (layout == "auto" and feats.shape[2] % (4 if feats.dtype == torch.float32 else 8) == 0):
+            feats = ops.to_channels_last5(feats)
+        H_img, W_img = int(img_size[0]), int(img_size[1])
+        xs_k, ys_k = self._corner_axes(feats.device)
+        xs_g, ys_g = self._ground_axes(feats.device)
+        pv_k = ops.warp_fuse(feats, K, Rt, xs_k, ys_k, H_img, W_img, _lib.NONE | (_lib.FLAG_KORNIA_GEOMETRY << 8), False, 0)
+        pv_g = ops.warp_fuse(feats, K, Rt, xs_g, ys_g, H_img, W_img, _lib.NONE, False, 0)
+        pv = torch.where(sing[:, :, None, None, None], pv_g, pv_k)
+        if mode == _lib.NONE:
+            return pv
+        name = {v: k for k, v in _lib.MODES.items() if k != "concat"}[mode]
+        out = ops.fuse_views_autograd(pv, name) if pv.requires_grad else ops.fuse_views(pv, name)
+        return out.bfloat16() if out_bf16 else out
+
+
 class GeometryTransformer(_IPMBase):
     """Per-view IPM warp, drop-in for geometry.py:12-163 (grid_sample semantics)."""
 
     def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, warp_impl: str = "grid_sample", layout: str = "keep",
-                 emulate_kornia: bool = False):
+                 emulate_kornia: bool | None = None):
         super().__init__(bev_h, bev_w, bev_bounds)
         # geometry.py:20 -- both names are accepted; 'kornia' executes the grid_sample branch in any
-        # environment without kornia (this image), which is the behaviour mirrored here.  emulate_kornia=True
-        # (with warp_impl='kornia') instead reproduces the sample positions of the kornia branch
-        # (geometry.py:124-141) for users whose reference runs WITH kornia: BEV pixel j at the cell corner,
-        # source pixel p read at p*size/(size-1) - 0.5.  From kornia's published algorithm: parity unpinned.
+        # environment without kornia (this image) and the kornia branch where kornia imports: emulate_kornia=None
+        # (default) mirrors exactly that decision (_resolve_kornia).  The kornia-compatible mode reproduces the sample
+        # positions of geometry.py:124-141: BEV pixel j at the cell corner, source pixel p read at
+        # p*size/(size-1) - 0.5; a view whose matrix M is singular (|det| < 1e-8, geometry.py:134-136) falls back
+        # to the grid_sample geometry like the reference.  From kornia's published algorithm: parity unpinned.
         self.warp_impl = warp_impl if warp_impl in ("grid_sample", "kornia") else "grid_sample"
-        self.emulate_kornia = bool(emulate_kornia) and self.warp_impl == "kornia"
+        self.emulate_kornia = _resolve_kornia(self.warp_impl, emulate_kornia)
         self.layout = layout
         self._grid_cache = {}
 
@@ -186,25 +251,55 @@ class FusedIPM(_IPMBase):
 
     def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, fusion: str = "mean",
                  warp_impl: str = "grid_sample", out_dtype: torch.dtype = torch.float32,
-                 layout: str = "auto", variant: int = 0, emulate_kornia: bool = False):
+                 layout: str = "auto", variant: int = 0, emulate_kornia: bool | None = None, return_valid: bool = False):
         super().__init__(bev_h, bev_w, bev_bounds)
-        assert fusion in ("sum", "mean", "max", "concat", "none")
+        # "mean_valid": mean over the views that SEE a cell (opt-in extension; the reference's "mean" divides by V)
+        assert fusion in ("sum", "mean", "max", "concat", "none", "mean_valid")
         assert out_dtype in (torch.float32, torch.bfloat16)
         assert layout in ("auto", "keep", "channels_last")
         self.fusion = fusion
         self.warp_impl = warp_impl if warp_impl in ("grid_sample", "kornia") else "grid_sample"
-        self.emulate_kornia = bool(emulate_kornia) and self.warp_impl == "kornia"   # see GeometryTransformer
+        self.emulate_kornia = _resolve_kornia(self.warp_impl, emulate_kornia)   # see GeometryTransformer
         self.out_dtype = out_dtype
         self.layout = layout   # "auto": NCHW-contiguous features go through our transpose pre-pass
         self.variant = variant
+        self.return_valid = return_valid   # also return count [B,Hb,Wb] int32: views that see each cell
+
+    def valid_count(self, feats: torch.Tensor, intrinsics, extrinsics, img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
+        """count [B,Hb,Wb] int32 of the views whose sample position has a bilinear tap inside the feature map."""
+        B, V = feats.shape[:2]
+        K, Rt = pack_calibration(intrinsics, extrinsics, B, V, feats.device)
+        xs, ys = self._corner_axes(feats.device) if self.emulate_kornia else self._ground_axes(feats.device)
+        return ops.valid_count(K, Rt, xs, ys, tuple(feats.shape[-2:]), (int(img_size[0]), int(img_size[1])),
+                               _lib.FLAG_KORNIA_GEOMETRY if self.emulate_kornia else 0)
 
     def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
-                img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
-        out = self._run(feats, intrinsics, extrinsics, img_size, _lib.MODES[self.fusion],
-                        self.out_dtype == torch.bfloat16, self.variant, self.layout, self.emulate_kornia)
-        if self.fusion == "concat":
+                img_size: Tuple[int, int] = (1080, 1920)):
+        fusion = self.fusion
+        needs_grad = feats.requires_grad and torch.is_grad_enabled()
+        if fusion == "max" and needs_grad:
+            # the fused max kernel has no backward: per-view maps (our forward + backward) followed by our max reduction,
+            # whose backward routes the gradient to the first arg-max view like torch.max (fusion.py:22 is differentiable)
+            pv = self._run(feats, intrinsics, extrinsics, img_size, _lib.NONE, False, 0, self.layout, self.emulate_kornia)
+            out = ops.fuse_views_autograd(pv, "max")
+            out = out.to(self.out_dtype)
+        elif fusion == "mean_valid":
+            out = self._run(feats, intrinsics, extrinsics, img_size, _lib.SUM, False, self.variant, self.layout, self.emulate_kornia)
+            cnt = self.valid_count(feats, intrinsics, extrinsics, img_size)
+            if needs_grad:
+                out = out / cnt.clamp(min=1).to(out.dtype).unsqueeze(1)
+            else:
+                out = ops.divide_by_count_(out, cnt)
+            out = out.to(self.out_dtype)
+            return (out, cnt) if self.return_valid else out
+        else:
+            out = self._run(feats, intrinsics, extrinsics, img_size, _lib.MODES[fusion],
+                            self.out_dtype == torch.bfloat16, self.variant, self.layout, self.emulate_kornia)
+        if fusion == "concat":
             B, V, C, Hb, Wb = out.shape
-            return out.reshape(B, V * C, Hb, Wb)   # fusion.py:45-46, channel index v*C + c
+            out = out.reshape(B, V * C, Hb, Wb)   # fusion.py:45-46, channel index v*C + c
+        if self.return_valid:
+            return out, self.valid_count(feats, intrinsics, extrinsics, img_size)
         return out
 
 
@@ -251,7 +346,8 @@ class FusionModule(nn.Module):
 
 
 class SimpleFusion(FusionModule):
-    """fusion.py:11-22 on materialised per-view maps (our reduction kernel; mean divides by V)."""
+    """fusion.py:11-22 on materialised per-view maps (our reduction kernels, forward and backward; mean divides by V,
+    max sends the gradient to the first view holding the maximum like torch.max)."""
 
     def __init__(self, mode: str = "sum"):
         super().__init__()
@@ -260,12 +356,7 @@ class SimpleFusion(FusionModule):
 
     def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
         if bev_maps.requires_grad and torch.is_grad_enabled():
-            # the stand-alone reduction has no hand-written backward; autograd users take the fused module
-            if self.mode == "sum":
-                return bev_maps.sum(dim=1)
-            if self.mode == "mean":
-                return bev_maps.mean(dim=1)
-            return bev_maps.max(dim=1).values
+            return ops.fuse_views_autograd(bev_maps, self.mode)   # forward and backward on our kernels
         return ops.fuse_views(bev_maps, self.mode)
 
 

@@ -100,8 +100,13 @@ def _(feats, K, Rt34, xs, ys, img_h, img_w, mode, out_bf16, variant):
     B, V, C = feats.shape[:3]
     Hb, Wb = ys.numel(), xs.numel()
     dt = torch.bfloat16 if out_bf16 else torch.float32
-    shape = (B, V, C, Hb, Wb) if (mode & 0xff) == _lib.NONE else (B, C, Hb, Wb)
-    return feats.new_empty(shape, dtype=dt)
+    # same strides as the real op: channels-last in memory when the features are (_alloc_out)
+    per_view = (mode & 0xff) == _lib.NONE
+    if _is_channels_last5(feats):
+        if per_view:
+            return feats.new_empty((B, V, Hb, Wb, C), dtype=dt).permute(0, 1, 4, 2, 3)
+        return feats.new_empty((B, Hb, Wb, C), dtype=dt).permute(0, 3, 1, 2)
+    return feats.new_empty((B, V, C, Hb, Wb) if per_view else (B, C, Hb, Wb), dtype=dt)
 
 
 @torch.library.custom_op("bevipm::warp_fuse_bwd", mutates_args=(), device_types="cuda")
@@ -134,7 +139,10 @@ def warp_fuse_bwd(grad_out: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, x
 
 @warp_fuse_bwd.register_fake
 def _(grad_out, K, Rt34, xs, ys, feat_shape, channels_last, img_h, img_w, mode):
-    return grad_out.new_empty(tuple(feat_shape), dtype=torch.float32)
+    B, V, C, Hf, Wf = feat_shape
+    if channels_last:
+        return grad_out.new_empty((B, V, Hf, Wf, C), dtype=torch.float32).permute(0, 1, 4, 2, 3)
+    return grad_out.new_empty((B, V, C, Hf, Wf), dtype=torch.float32)
 
 
 def _setup_ctx(ctx, inputs, output):
@@ -224,6 +232,74 @@ def fuse_views(bev_maps: torch.Tensor, mode: str, out_dtype=None) -> torch.Tenso
         _lib.check(_lib.load().bevipm_fuse_views(_ptr(src), _ptr(out), B, V, C * H * W, MODES[mode], _DT[src.dtype],
                                                  _DT[out_dtype], ctypes.c_void_p(_stream_ptr(src.device))))
     return out.permute(0, 3, 1, 2) if cl else out
+
+
+def fuse_views_bwd(grad_out: torch.Tensor, mode: str, shape, channels_last: bool, bev_maps: torch.Tensor | None = None) -> torch.Tensor:
+    """Gradient of fuse_views w.r.t. the per-view maps (autograd of fusion.py:17-22): [B,V,C,H,W] float32, channels-last
+    in memory when the maps were.  max needs the forward input `bev_maps` and sends the gradient to the first view holding
+    the maximum (torch.max's rule)."""
+    B, V, C, H, W = shape
+    cl = channels_last
+    src = None
+    if mode == "max":
+        src = (bev_maps.permute(0, 1, 3, 4, 2) if cl else bev_maps).contiguous()
+    g = (grad_out.permute(0, 2, 3, 1) if cl else grad_out).to(torch.float32).contiguous()
+    gin = torch.empty((B, V, H, W, C) if cl else (B, V, C, H, W), device=g.device, dtype=torch.float32)
+    with torch.cuda.device(g.device):
+        _lib.check(_lib.load().bevipm_fuse_views_bwd(_ptr(src) if src is not None else None, _ptr(g), _ptr(gin), B, V, C * H * W,
+                                                     MODES[mode], _DT[src.dtype] if src is not None else _lib.F32,
+                                                     ctypes.c_void_p(_stream_ptr(g.device))))
+    return gin.permute(0, 1, 4, 2, 3) if cl else gin
+
+
+class _FuseViews(torch.autograd.Function):
+    """SimpleFusion on our kernels in both directions (bevipm_fuse_views / bevipm_fuse_views_bwd)."""
+
+    @staticmethod
+    def forward(ctx, bev_maps, mode):
+        ctx.mode = mode
+        ctx.meta = (tuple(bev_maps.shape), _is_channels_last5(bev_maps) and not bev_maps.is_contiguous(), bev_maps.dtype)
+        if mode == "max":
+            ctx.save_for_backward(bev_maps)
+        return fuse_views(bev_maps, mode)
+
+    @staticmethod
+    def backward(ctx, grad):
+        shape, cl, dtype = ctx.meta
+        src = ctx.saved_tensors[0].detach() if ctx.mode == "max" else None
+        return fuse_views_bwd(grad, ctx.mode, shape, cl, src).to(dtype), None
+
+
+def fuse_views_autograd(bev_maps: torch.Tensor, mode: str) -> torch.Tensor:
+    return _FuseViews.apply(bev_maps, mode)
+
+
+def valid_count(K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor, feat_hw: Tuple[int, int],
+                img_size: Tuple[int, int], flags: int = 0) -> torch.Tensor:
+    """count [B,Hb,Wb] int32: how many views see each BEV cell (at least one bilinear tap inside the feature map).
+    The validity-mask count of the north star; an extension (the reference's mean divides by V, fusion.py:20-21)."""
+    B, V = K.shape[:2]
+    Hb, Wb = ys.numel(), xs.numel()
+    cnt = torch.empty((B, Hb, Wb), device=K.device, dtype=torch.int32)
+    d = _fill_desc((B, V, 1, feat_hw[0], feat_hw[1]), (0,) * 5, (0,) * 5, (Hb, Wb), img_size, 0, 0, 0, 0, flags)
+    with torch.cuda.device(K.device):
+        _lib.check(_lib.load().bevipm_valid_count(ctypes.byref(d), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys), _ptr(cnt),
+                                                  ctypes.c_void_p(_stream_ptr(K.device))))
+    return cnt
+
+
+def divide_by_count_(bev_sum: torch.Tensor, count: torch.Tensor) -> torch.Tensor:
+    """In place: bev_sum [B,C,Hb,Wb] float32 (a SUM-mode result) /= max(count, 1): the mean over the views that see each
+    cell.  Opt-in extension, NOT the reference's mean."""
+    if bev_sum.dtype != torch.float32 or bev_sum.dim() != 4:
+        raise ValueError("divide_by_count_ wants the float32 [B,C,Hb,Wb] result of sum fusion")
+    B, C, Hb, Wb = bev_sum.shape
+    s = bev_sum.stride()
+    d = _fill_desc((B, 1, C, 1, 1), (0,) * 5, (s[0], 0, s[1], s[2], s[3]), (Hb, Wb), (1, 1), 0, 0, 0, 0)
+    with torch.cuda.device(bev_sum.device):
+        _lib.check(_lib.load().bevipm_divide_by_count(ctypes.byref(d), _ptr(bev_sum), _ptr(count.contiguous()),
+                                                      ctypes.c_void_p(_stream_ptr(bev_sum.device))))
+    return bev_sum
 
 
 def warp_fuse_host(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,

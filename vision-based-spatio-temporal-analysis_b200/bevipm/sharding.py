@@ -75,7 +75,7 @@ class ViewShardedFusion:
 
     def finish(self, reduced: torch.Tensor) -> torch.Tensor:
         if self.mode == "mean":
-            reduced.div_(float(self.views))
+            reduced.div_(torch.tensor(float(self.views), device=reduced.device))   # tensor divisor: IEEE division on CUDA too
         return reduced
 
 
@@ -101,3 +101,133 @@ def gather_frames(local: torch.Tensor, frames: int, group=None) -> torch.Tensor:
     outs = [torch.empty_like(buf) for _ in range(world)]
     dist.all_gather(outs, buf, group=group)
     return torch.cat([o[:n] for o, n in zip(outs, sizes)], dim=0)
+
+
+# ---- view sharding that leaves the BEV sharded by rows --------------------------------------------------
+# The all-reduce above replicates the whole fp32 BEV on every rank: 2 (N-1)/N x 354 MB per rank and frame at BASELINE
+# configs[2], more than the single-GPU kernel reads and writes.  The consumer of a BEV grid (detector head, the next
+# fusion stage) is itself row-separable, so the two forms below leave rank r with rows [r * Hb/N, (r+1) * Hb/N) only:
+# (N-1)/N x 354 MB per rank and frame cross NVLink, once.
+
+def slab_rows(bev_h: int, world: int) -> int:
+    """BEV rows per rank (the last slab is padded when world does not divide bev_h)."""
+    return -(-bev_h // world)
+
+
+class ReduceScatterFusion:
+    """Partial BEV per rank -> NCCL reduce-scatter -> this rank's row slab, on a side stream.
+
+    submit(part) queues the collective behind the kernel that produced `part` and returns at once, so the warp of frame
+    t+1 (current stream) overlaps the reduce-scatter of frame t (side stream); wait(ticket) returns the finished slab
+    [B,C,rows,Wb] fp32 (channels-last in memory) and orders the current stream after it.
+    """
+
+    def __init__(self, views: int, bev_hw, channels: int, mode: str = "mean", group=None, device=None):
+        if mode not in ("sum", "mean"):
+            raise ValueError("reduce-scatter view sharding supports sum / mean")
+        self.views, self.mode, self.group = views, mode, group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.Hb, self.Wb = bev_hw
+        self.C = channels
+        self.rows = slab_rows(self.Hb, self.world)
+        self.device = device
+        self.side = torch.cuda.Stream(device=device)
+        self._div = None
+
+    def submit(self, part: torch.Tensor):
+        """part: this rank's partial sum [B,C,Hb,Wb] fp32, channels-last in memory (what ops.warp_fuse returns)."""
+        B = part.shape[0]
+        mem = part.permute(0, 2, 3, 1)                       # [B,Hb,Wb,C] as it lies in memory
+        if not mem.is_contiguous():
+            raise ValueError("partial BEV must be channels-last")
+        pad = self.rows * self.world - self.Hb
+        if pad:
+            mem = torch.cat([mem, mem.new_zeros(B, pad, self.Wb, self.C)], dim=1)
+        out = torch.empty((B, self.rows, self.Wb, self.C), device=part.device, dtype=torch.float32)
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            for b in range(B):                               # a frame's row slabs are contiguous: one collective per frame
+                dist.reduce_scatter_tensor(out[b], mem[b], op=dist.ReduceOp.SUM, group=self.group)
+            if self.mode == "mean":
+                if self._div is None:
+                    self._div = torch.tensor(float(self.views), device=part.device)
+                out.div_(self._div)                          # tensor divisor: IEEE division (fusion.py:20-21 divides by V)
+            done = torch.cuda.Event()
+            done.record()
+        mem.record_stream(self.side)
+        return out, done
+
+    def wait(self, ticket) -> torch.Tensor:
+        out, done = ticket
+        torch.cuda.current_stream().wait_event(done)
+        out.record_stream(torch.cuda.current_stream())
+        return out.permute(0, 3, 1, 2)                       # logical [B,C,rows,Wb]
+
+
+class PeerSlabFusion:
+    """Fused compute + exchange: every rank's warp kernel adds its partial sum straight into the row slabs of their
+    owners through peer memory (bevipm_warp_fuse_red: red.global.add.v4.f32 on NVLink-mapped pointers from torch's
+    symmetric memory), so the partial BEV is never written to or re-read from local HBM and the transfer overlaps the
+    warp tile by tile.  Two slab buffers alternate, so zeroing the next one is off the critical path.
+
+    run(feats_r, K_r, Rt_r, xs, ys, img_size) -> this rank's slab [B,C,rows,Wb] fp32 (valid until the call after next).
+    """
+
+    def __init__(self, views: int, bev_hw, channels: int, frames: int = 1, mode: str = "mean", group=None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if mode not in ("sum", "mean"):
+            raise ValueError("peer-slab view sharding supports sum / mean")
+        self.views, self.mode = views, mode
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.Hb, self.Wb = bev_hw
+        self.C, self.B = channels, frames
+        self.rows = slab_rows(self.Hb, self.world)
+        try:
+            symm_mem.enable_symm_mem_for_group(self.group.group_name)
+        except Exception:
+            pass
+        self.buf = symm_mem.empty((2, frames, self.rows, self.Wb, channels), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.buf.zero_()
+        self.turn = 0
+        self._div = torch.tensor(float(views), device=device)
+        self.hdl.barrier()
+
+    def bytes_over_nvlink_per_call(self) -> int:
+        """fp32 bytes this rank adds into OTHER ranks' slabs per call (what crosses NVLink)."""
+        own = min(self.rows, max(0, self.Hb - self.rank * self.rows))
+        return self.B * (self.Hb - own) * self.Wb * self.C * 4
+
+    def run(self, feats_r, K_r, Rt_r, xs, ys, img_size):
+        import ctypes
+        from . import _lib, ops
+        k = self.turn
+        self.turn ^= 1
+        slab = self.buf[k]
+        stream = torch.cuda.current_stream()
+        # Slab k was zeroed by its owner right after its previous use, two calls ago (or at construction): the closing
+        # barrier of the call in between already ordered every rank's zeroing before any rank's adds of this call.
+        if feats_r is not None and feats_r.shape[1] > 0:
+            B, V, C, Hf, Wf = feats_r.shape
+            if not ops._is_channels_last5(feats_r):
+                raise ValueError("PeerSlabFusion wants channels-last features")
+            d = ops._fill_desc(feats_r.shape, feats_r.stride(), (self.rows * self.Wb * self.C, 0, 1, self.Wb * self.C, self.C),
+                               (self.Hb, self.Wb), (int(img_size[0]), int(img_size[1])), _lib.SUM, ops._DT[feats_r.dtype], _lib.F32, 0)
+            off = k * self.B * self.rows * self.Wb * self.C * 4
+            arr = (ctypes.c_void_p * self.world)(*[p + off for p in self.ptrs])
+            _lib.check(_lib.load().bevipm_warp_fuse_red(ctypes.byref(d), ops._ptr(feats_r), ops._ptr(K_r), ops._ptr(Rt_r), ops._ptr(xs),
+                                                        ops._ptr(ys), arr, self.world, self.rows, ctypes.c_void_p(stream.cuda_stream)))
+        self.hdl.barrier()                                    # every rank's adds have landed in my slab
+        out = slab.permute(0, 3, 1, 2)                        # logical [B,C,rows,Wb]
+        if self.mode == "mean":
+            out = out / self._div                             # IEEE division by V on the owner's rows (fusion.py:20-21)
+        else:
+            out = out.clone()
+        slab.zero_()                                          # ready for its next turn (two calls from now)
+        return out

@@ -71,6 +71,8 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
     p.fsy16 = p.fsx16 = 0;
     p.rcpV = 0.0f;
     p.kx = p.ky = 0.0f;
+    for (int q = 0; q < 16; ++q) p.slab[q] = nullptr;
+    p.slab_rows = 1;
     if (d->flags & BEVIPM_FLAG_KORNIA_GEOMETRY) {
         p.kx = d->Wf > 1 ? (float)((double)d->Wf / (double)(d->Wf - 1)) : 1.0f;
         p.ky = d->Hf > 1 ? (float)((double)d->Hf / (double)(d->Hf - 1)) : 1.0f;
@@ -333,6 +335,19 @@ int launch_deform(const bevipm::DeformParams& p, int lph, cudaStream_t st) {
 }  // namespace
 
 
+namespace bevipm {
+// for the launchers that live in other translation units (bevipm_shard.cu)
+void note_launch(int variant) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_last_variant = variant;
+}
+int set_error(int code, const char* msg) { return fail(code, "%s", msg); }
+FwdParams params_from_desc(const bevipm_desc* d, const void* feats, const float* K, const float* Rt, const float* xs, const float* ys, void* out) {
+    return make_params(d, feats, K, Rt, xs, ys, out);
+}
+int check_desc_public(const bevipm_desc* d) { return check_desc(d); }
+}  // namespace bevipm
+
 extern "C" {
 
 int bevipm_version(void) { return BEVIPM_VERSION; }
@@ -471,6 +486,48 @@ int bevipm_fuse_views(const void* in, void* out, int64_t B, int32_t V, int64_t i
     return 0;
 }
 
+int bevipm_fuse_views_bwd(const void* in, const float* grad_out, float* grad_in, int64_t B, int32_t V, int64_t inner, int32_t mode,
+                          int32_t in_dtype, void* stream) {
+    if (!grad_out || !grad_in) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (B <= 0 || V <= 0 || inner <= 0) return fail(BEVIPM_ERR_BAD_ARG, "non-positive extent");
+    if (mode < BEVIPM_SUM || mode > BEVIPM_MAX) return fail(BEVIPM_ERR_BAD_ARG, "mode must be sum, mean or max");
+    if (mode == BEVIPM_MAX && !in) return fail(BEVIPM_ERR_BAD_ARG, "max needs the forward input");
+    if (B > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B exceeds gridDim.y");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long want = (inner + 255) / 256;
+    dim3 grid((unsigned)(want < 148 * 32 ? want : 148 * 32), (unsigned)B);
+    if (in_dtype == BEVIPM_BF16) bevipm::fuse_views_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)in, grad_out, grad_in, V, inner, mode);
+    else bevipm::fuse_views_bwd_kernel<float><<<grid, 256, 0, st>>>((const float*)in, grad_out, grad_in, V, inner, mode);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bevipm_valid_count(const bevipm_desc* d, const float* K, const float* Rt34, const float* xs, const float* ys, int32_t* count,
+                       void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (!K || !Rt34 || !xs || !ys || !count) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    const FwdParams p = make_params(d, nullptr, K, Rt34, xs, ys, nullptr);
+    dim3 grid(ceil_div(d->Hb * d->Wb, 256), (unsigned)d->B);
+    bevipm::valid_count_kernel<<<grid, 256, (size_t)d->V * 9 * sizeof(float), static_cast<cudaStream_t>(stream)>>>(p, count);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int bevipm_divide_by_count(const bevipm_desc* d, float* bev, const int32_t* count, void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (!bev || !count) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (d->out_dtype != BEVIPM_F32) return fail(BEVIPM_ERR_UNSUPPORTED, "divide_by_count works on the f32 SUM result");
+    const long long blocks = (long long)d->B * d->Hb * d->Wb;  // one block per (frame, cell)
+    if (blocks > 0x7fffffffLL) return fail(BEVIPM_ERR_UNSUPPORTED, "BEV too large");
+    bevipm::divide_by_count_kernel<<<(unsigned)blocks, 128, 0, static_cast<cudaStream_t>(stream)>>>(bev, count, d->C, d->Hb, d->Wb, d->os_b, d->os_c,
+                                                                                                   d->os_y, d->os_x);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int bevipm_deform_attn_fwd(const bevipm_deform_desc* d, const void* value, const int32_t* shapes, const int64_t* level_start,
                            const float* loc, const float* attn, void* out, void* stream) {
     if (!d) return fail(BEVIPM_ERR_BAD_ARG, "desc is null");
@@ -506,6 +563,7 @@ struct HostArena {
     int* rows = nullptr;        // device: touched x-span per (frame, view, source row)
     int* rows_host = nullptr;   // pinned host copy
     size_t rows_count = 0;
+    uint64_t span_key = 0;      // hash of the calibration + shapes the cached span table belongs to (0 = none)
     size_t feat_bytes = 0, out_bytes = 0, calib_bytes = 0;
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t calib_ready = nullptr;
@@ -521,12 +579,28 @@ struct HostArena {
         if (rows) cudaFree(rows);
         if (rows_host) cudaFreeHost(rows_host);
         if (calib_ready) cudaEventDestroy(calib_ready);
-        calib = nullptr; calib_ready = nullptr; rows = nullptr; rows_host = nullptr; rows_count = 0;
+        calib = nullptr; calib_ready = nullptr; rows = nullptr; rows_host = nullptr; rows_count = 0; span_key = 0;
         feat_bytes = out_bytes = calib_bytes = 0; device = -1;
     }
 };
 thread_local HostArena g_arena;
 thread_local int64_t g_host_h2d_bytes = 0;
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
+// On any failure after copies were queued: the caller's buffers and the arena must be quiet before we return.
+struct StreamQuiet {
+    HostArena& a;
+    bool armed = true;
+    ~StreamQuiet() {
+        if (!armed) return;
+        for (int s = 0; s < 2; ++s) if (a.st[s]) cudaStreamSynchronize(a.st[s]);
+    }
+};
 }  // namespace
 
 void bevipm_host_release(void) { g_arena.release(); }
@@ -559,6 +633,10 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
         CUDA_TRY(cudaEventCreateWithFlags(&A.calib_ready, cudaEventDisableTiming));
         A.feat_bytes = fbytes; A.out_bytes = obytes; A.calib_bytes = cal_floats * 4; A.rows_count = nbv; A.device = dev;
     }
+    // shape limits of the span kernel are checked before anything is queued
+    if ((size_t)d.B * d.V > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B*V too large");
+    if ((size_t)d.Hf * 8 > 40 * 1024) return fail(BEVIPM_ERR_UNSUPPORTED, "Hf=%d too tall for the span table of the host entry", d.Hf);
+    StreamQuiet quiet{A};
     float* dK = A.calib;
     float* dRt = dK + (size_t)d.B * d.V * 9;
     float* dxs = dRt + (size_t)d.B * d.V * 12;
@@ -569,14 +647,26 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     CUDA_TRY(cudaMemcpyAsync(dys, ys, (size_t)d.Hb * 4, cudaMemcpyHostToDevice, A.st[0]));
     // Which source texels does any BEV cell sample?  Only those are uploaded (rows above the horizon of a ground-plane
     // homography, and the part of a row outside the BEV patch, are never read by the kernels): one small launch and
-    // an 8-byte-per-source-row read-back before the first copy.
+    // an 8-byte-per-source-row read-back before the first copy -- once per calibration: cameras are static
+    // (wildtrack_loader.py:291-293), so the table is kept for as long as calibration, axes and shapes repeat bit for bit
+    // (the `_grid_cache` the reference declares and never fills, geometry.py:22).
+    uint64_t key = 1469598103934665603ULL;
     {
+        const int32_t dims[12] = {d.B, d.V, d.Hf, d.Wf, d.Hb, d.Wb, d.img_h, d.img_w, d.flags, 0, 0, 0};
+        key = fnv1a(key, dims, sizeof(dims));
+        key = fnv1a(key, K, (size_t)d.B * d.V * 9 * 4);
+        key = fnv1a(key, Rt34, (size_t)d.B * d.V * 12 * 4);
+        key = fnv1a(key, xs, (size_t)d.Wb * 4);
+        key = fnv1a(key, ys, (size_t)d.Hb * 4);
+        if (key == 0) key = 1;
+    }
+    const bool spans_cached = A.span_key == key;
+    if (!spans_cached) {
+        A.span_key = 0;
         for (size_t q = 0; q < nbv; ++q) { A.rows_host[2 * q] = 0x7fffffff; A.rows_host[2 * q + 1] = -1; }
         CUDA_TRY(cudaMemcpyAsync(A.rows, A.rows_host, nbv * 2 * sizeof(int), cudaMemcpyHostToDevice, A.st[0]));
         FwdParams pr = make_params(&d, nullptr, dK, dRt, dxs, dys, nullptr);
         dim3 grid(ceil_div(d.Hb * d.Wb, 256), (unsigned)(d.B * d.V));
-        if (grid.y > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B*V too large");
-        if ((size_t)d.Hf * 8 > 40 * 1024) return fail(BEVIPM_ERR_UNSUPPORTED, "Hf=%d too tall for the span table of the host entry", d.Hf);
         bevipm::touched_spans_kernel<<<grid, 256, (size_t)d.Hf * 2 * sizeof(int), A.st[0]>>>(pr, A.rows);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
@@ -584,7 +674,10 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     }
     CUDA_TRY(cudaEventRecord(A.calib_ready, A.st[0]));
     CUDA_TRY(cudaStreamWaitEvent(A.st[1], A.calib_ready, 0));
-    CUDA_TRY(cudaStreamSynchronize(A.st[0]));  // the row ranges are needed on the host now
+    if (!spans_cached) {
+        CUDA_TRY(cudaStreamSynchronize(A.st[0]));  // the row ranges are needed on the host now
+        A.span_key = key;
+    }
     // one frame per launch, channels-last on the device
     const int B = d.B;
     d.B = 1;
@@ -622,6 +715,7 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     g_host_h2d_bytes = h2d + (int64_t)cal_floats * 4;
     CUDA_TRY(cudaStreamSynchronize(A.st[0]));
     CUDA_TRY(cudaStreamSynchronize(A.st[1]));
+    quiet.armed = false;
     return 0;
 }
 

@@ -217,6 +217,68 @@ __global__ void __launch_bounds__(256) fuse_views_kernel(const TIn* __restrict__
     }
 }
 
+// Backward of fuse_views_kernel: grad_in[b,v,e] from grad_out[b,e].  sum: g; mean: g / V; max: g to the FIRST view that
+// holds the maximum (torch.max's index rule), 0 to the others; a NaN maximum sends g to the first NaN view.
+template <typename TIn>
+__global__ void __launch_bounds__(256) fuse_views_bwd_kernel(const TIn* __restrict__ in, const float* __restrict__ gout,
+                                                             float* __restrict__ gin, int V, long long inner, int mode) {
+    const long long b = blockIdx.y;
+    const TIn* ib = in + b * V * inner;
+    float* gb = gin + b * V * inner;
+    const float Vf = (float)V;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < inner; e += (long long)gridDim.x * blockDim.x) {
+        const float g = gout[b * inner + e];
+        if (mode == 2) {
+            float best = load_f32(ib + e);
+            int arg = 0;
+            for (int v = 1; v < V; ++v) {
+                const float s = load_f32(ib + (long long)v * inner + e);
+                if (best == best && (s > best || s != s)) { best = s; arg = v; }
+            }
+            for (int v = 0; v < V; ++v) gb[(long long)v * inner + e] = v == arg ? g : 0.0f;
+        } else {
+            const float gv = mode == 1 ? __fdiv_rn(g, Vf) : g;
+            for (int v = 0; v < V; ++v) gb[(long long)v * inner + e] = gv;
+        }
+    }
+}
+
+// Validity mask count (north star: "validity-mask counts"): count[b,i,j] = number of views whose sample position of BEV
+// cell (i, j) has at least one bilinear tap inside the feature map (the cells geometry.py:161 reads non-padding from).
+// One warp per 32 cells of a row, views looped; same projection and tap test as the fused kernels.
+__global__ void __launch_bounds__(256) valid_count_kernel(const FwdParams p, int* __restrict__ count) {
+    extern __shared__ float s_h[];  // [V][9]
+    const int b = blockIdx.y;
+    for (int v = threadIdx.x; v < p.V; v += blockDim.x) homography(p.K + 9 * (b * p.V + v), p.Rt + 12 * (b * p.V + v), s_h + 9 * v);
+    __syncthreads();
+    const int cell = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= p.Hb * p.Wb) return;
+    const int i = cell / p.Wb, j = cell - i * p.Wb;
+    const float x = p.xs[j], y = p.ys[i];
+    int n = 0;
+    for (int v = 0; v < p.V; ++v) {
+        float ix, iy;
+        cell_coord(s_h + 9 * v, x, y, p.sw, p.sh, (float)p.Wf, (float)p.Hf, ix, iy, p.kx, p.ky);
+        n += (make_tap(ix, iy, p.Wf, p.Hf).flags & kTapMask) != 0;
+    }
+    count[(long long)b * p.Hb * p.Wb + cell] = n;
+}
+
+// Mean over the views that SEE a cell (opt-in extension; the reference's mean divides by V, fusion.py:20-21):
+// bev[b,i,j,c] (a SUM-mode result, fp32, element strides os_*) /= max(count[b,i,j], 1), IEEE division.
+__global__ void __launch_bounds__(128) divide_by_count_kernel(float* __restrict__ bev, const int* __restrict__ count, int C, int Hb, int Wb,
+                                                              long long os_b, long long os_c, long long os_y, long long os_x) {
+    const long long bc = blockIdx.x;  // (frame, cell)
+    const int cells = Hb * Wb;
+    const int b = (int)(bc / cells), cell = (int)(bc - (long long)b * cells);
+    const int n = count[bc];
+    if (n <= 1) return;
+    const int i = cell / Wb, j = cell - i * Wb;
+    const float nf = (float)n;
+    float* o = bev + (long long)b * os_b + (long long)i * os_y + (long long)j * os_x;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) o[(long long)c * os_c] = __fdiv_rn(o[(long long)c * os_c], nf);
+}
+
 // [N,C,HW] -> [N,HW,C]   (the encoder's NCHW maps, cnn_encoder.py:65-70, into the fast path's layout)
 template <typename T>
 __global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int C, int HW) {

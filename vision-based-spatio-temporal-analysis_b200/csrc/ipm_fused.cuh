@@ -46,9 +46,14 @@ struct FwdParams {
     int fsy16, fsx16;    // fs_y, fs_x in 16-byte units (fast path)
     float rcpV;          // RN(1 / V) for the exact mean division
     float kx, ky;        // 0 = reference grid_sample geometry; Wf/(Wf-1), Hf/(Hf-1) = kornia-compatible sample positions
+    // KM_RED (view sharding over peer memory): BEV rows [q * slab_rows, (q + 1) * slab_rows) live in slab[q], the
+    // fp32 buffer of the rank that owns them (its own memory or a peer's, mapped over NVLink); strides os_* are a slab's
+    void* slab[16];
+    int slab_rows;
 };
 
-enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2, KM_PROBE = 3 /* timing probe: loads only, no blend */ };
+enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2, KM_PROBE = 3 /* timing probe: loads only, no blend */,
+       KM_RED = 4 /* sum over this rank's views, ADDED (red.global.add) into the row slab of the owning rank */ };
 
 // ---- 16-byte vector <-> fp32 pairs -------------------------------------------------------
 template <typename T> struct VecTraits;
@@ -101,6 +106,15 @@ __device__ __forceinline__ void store_pairs(TOut* dst, const float2 (&f)[P]) {
             __stcs(reinterpret_cast<uint2*>(dst), make_uint2(w[0], w[1]));
         }
     }
+}
+
+// P float2 pairs ADDED to fp32 global memory (local or peer) with 16-byte reductions: the partial sum of one rank's views
+// goes straight into the owner's slab, it never lands in this rank's HBM
+template <int P>
+__device__ __forceinline__ void red_pairs(float* dst, const float2 (&f)[P]) {
+#pragma unroll
+    for (int k = 0; k < P; k += 2)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 2 * k), "f"(f[k].x), "f"(f[k].y), "f"(f[k + 1].x), "f"(f[k + 1].y) : "memory");
 }
 
 // x / V, correctly rounded, in three FMA-pipe ops instead of the ~10-instruction IEEE division

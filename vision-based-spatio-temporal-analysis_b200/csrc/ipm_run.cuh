@@ -581,6 +581,19 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                         }
                 }
             }
+            if constexpr (KMODE == KM_RED) {
+                // view sharding: add this rank's partial sum into the slab of the rank that owns BEV row i (peer memory)
+                if (!lok) continue;
+                const int owner = i / p.slab_rows;
+                float* oc = reinterpret_cast<float*>(p.slab[owner]) + (long long)(b_run + fi_this) * p.os_b +
+                            (long long)(i - owner * p.slab_rows) * p.os_y + (long long)j0 * p.os_x + (k_this * 32 + lane) * VE;
+#pragma unroll
+                for (int c = 0; c < CELLS; ++c) {
+                    if (j0 + c < p.Wb) red_pairs<P>(oc, acc[c]);
+                    oc += p.os_x;
+                }
+                continue;
+            }
             TOut* oc = reinterpret_cast<TOut*>(p.out) + (long long)(b_run + fi_this) * p.os_b + (long long)i * p.os_y + (long long)j0 * p.os_x +
                        (k_this * 32 + lane) * VE;
             if (!lok) continue;
