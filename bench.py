@@ -664,6 +664,7 @@ def run_ours(args, wl):
         barrier()
     clocks = sampler.stop() if sampler else None
 
+    feat_bytes = feats.numel() * feats.element_size()
     # ---- informational blocks (outside every timed region) -----------------------------------------------------------
     extras = {}
     if not args.no_extras and not views_mode:
@@ -707,8 +708,8 @@ def run_ours(args, wl):
                 "parallelism": (f"views: {V} cameras split over {world} ranks "
                                 f"{[len(a) for a in sharding.view_assignment(V, world)]}, partial BEV (fp32) + NCCL all-reduce")
                 if views_mode else f"frames: {world} x {B} independent frames, no data-path collective",
-                "l2": "inputs larger than L2 (features %.2f GB per step vs 126 MB L2)" % (feats.numel() * feats.element_size() / 1e9)
-                      if feats.numel() * feats.element_size() > 256e6 else "inputs fit L2: see DESIGN.md",
+                "l2": "inputs larger than L2 (features %.2f GB per step vs 126 MB L2)" % (feat_bytes / 1e9)
+                      if feat_bytes > 256e6 else "inputs fit L2: see DESIGN.md",
                 "variant": args.variant, "arithmetic": "fp32 (bit-exact op chain of the reference), storage as named"}),
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

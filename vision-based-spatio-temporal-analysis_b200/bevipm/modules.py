@@ -96,7 +96,7 @@ def _resolve_kornia(warp_impl: str, emulate_kornia) -> bool:
     if emulate_kornia and not _KORNIA_NOTE:
         _KORNIA_NOTE = True
         import warnings
-        warnings.warn("bevipm: warp_impl='kornia' with kornia importable: using the kornia-compatible sample positions "
+        warnings.warn("bevipm: warp_impl='kornia': using the kornia-compatible sample positions "
                       "(BEV pixel at the cell corner, source pixel p read at p*size/(size-1) - 0.5).  This mode restates kornia's "
                       "published warp_perspective and is NOT pinned against a kornia build; pass emulate_kornia=False for the "
                       "reference's grid_sample geometry.", stacklevel=3)

@@ -187,10 +187,6 @@ class PeerSlabFusion:
         self.Hb, self.Wb = bev_hw
         self.C, self.B = channels, frames
         self.rows = slab_rows(self.Hb, self.world)
-        try:
-            symm_mem.enable_symm_mem_for_group(self.group.group_name)
-        except Exception:
-            pass
         self.buf = symm_mem.empty((2, frames, self.rows, self.Wb, channels), dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]

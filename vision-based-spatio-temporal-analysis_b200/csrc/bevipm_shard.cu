@@ -1,5 +1,6 @@
 // bevipm_shard.cu -- view sharding over peer memory: the fused warp kernel of one rank's cameras ADDS its partial sum
-// straight into the BEV row slabs of the ranks that own them (red.global.add.v4.f32 on NVLink-mapped peer pointers), so
+// straight into the BEV row slabs of the ranks that own them (bulk reductions, cp.reduce.async.bulk add.f32, on NVLink-mapped
+// peer pointers), so
 // the partial BEV never exists in this rank's HBM and the exchange overlaps the warp, tile by tile.
 // (BASELINE configs[2] / SURVEY.md 8(e): "views sharded ... with NCCL sum-reduce"; the NCCL forms are in bevipm/sharding.py.)
 #include <algorithm>
@@ -24,7 +25,9 @@ int launch_red(FwdParams p, cudaStream_t st) {
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
     auto kern = warp_fuse_run_kernel<TIn, float, CELLS, NW, 1, MAXREG, DEPTH, false, 0, KM_RED>;
-    const size_t smem = (size_t)run_tables_bytes(p.V, CELLS, NW) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8;
+    // tables, rings, homographies, (ring barriers), then one parking area of 8 cells x one chunk of fp32 sums per warp
+    const size_t smem = ((size_t)run_tables_bytes(p.V, CELLS, NW) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8 + 127) / 128 * 128 +
+                        (size_t)NW * CELLS * (32 * VE * 4);
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(BEVIPM_ERR_CUDA, "cudaFuncSetAttribute (red kernel)");
     int fpc = 1;

@@ -582,15 +582,36 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 }
             }
             if constexpr (KMODE == KM_RED) {
-                // view sharding: add this rank's partial sum into the slab of the rank that owns BEV row i (peer memory)
-                if (!lok) continue;
-                const int owner = i / p.slab_rows;
-                float* oc = reinterpret_cast<float*>(p.slab[owner]) + (long long)(b_run + fi_this) * p.os_b +
-                            (long long)(i - owner * p.slab_rows) * p.os_y + (long long)j0 * p.os_x + (k_this * 32 + lane) * VE;
+                // View sharding: this rank's partial sum goes into the slab of the rank that owns BEV row i (its own memory
+                // or a peer's over NVLink).  The warp parks its 8 cells x one chunk of fp32 sums in shared memory and hands
+                // them to the copy engine as bulk reductions (cp.reduce.async.bulk ... add.f32): kilobyte packets over the
+                // link instead of one 16-byte atomic per lane, and the kernel does not wait for them.
+                constexpr int CB = 32 * VE * 4;  // bytes of one cell's chunk of fp32 sums (512 for fp32, 1024 for bf16 features)
+                unsigned char* stg = smem_run + ((run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048) + V * 48 + NW * DEPTH * 8 + 127) / 128) * 128 +
+                                     warp * (CELLS * CB);
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the previous item's sums have left
+                __syncwarp();
 #pragma unroll
-                for (int c = 0; c < CELLS; ++c) {
-                    if (j0 + c < p.Wb) red_pairs<P>(oc, acc[c]);
-                    oc += p.os_x;
+                for (int c = 0; c < CELLS; ++c)
+#pragma unroll
+                    for (int q = 0; q < P; q += 2)
+                        *reinterpret_cast<float4*>(stg + c * CB + lane * (VE * 4) + q * 8) = make_float4(acc[c][q].x, acc[c][q].y, acc[c][q + 1].x, acc[c][q + 1].y);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    const int owner = i / p.slab_rows;
+                    float* oc = reinterpret_cast<float*>(p.slab[owner]) + (long long)(b_run + fi_this) * p.os_b +
+                                (long long)(i - owner * p.slab_rows) * p.os_y + (long long)j0 * p.os_x + k_this * 32 * VE;
+                    const int ch = min(32 * VE, p.C - k_this * 32 * VE);       // channels of this chunk that exist
+                    const int ncell = min(CELLS, p.Wb - j0);
+                    const uint32_t src = (uint32_t)__cvta_generic_to_shared(stg);
+                    if (ch * 4 == CB && p.os_x == 32 * VE) {                      // one chunk per texel: the cells are contiguous
+                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(oc), "r"(src), "r"(ncell * CB) : "memory");
+                    } else {
+                        for (int c = 0; c < ncell; ++c)
+                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(oc + (long long)c * p.os_x), "r"(src + c * CB), "r"(ch * 4) : "memory");
+                    }
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
                 continue;
             }
@@ -611,6 +632,9 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                 }
             }
         }
+    }
+    if constexpr (KMODE == KM_RED) {
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every bulk reduction of this warp has been performed
     }
 }
 
