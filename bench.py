@@ -477,19 +477,36 @@ def view_sharded_block(dev, world: int, rank: int, steps: int = 30):
     out["reduce_scatter_overlapped"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "nvlink_bytes_per_rank": int(sent),
                                         "nvlink_gbs_per_rank": sent / ms / 1e6, "result": f"{sharding.slab_rows(Hb, world)} BEV rows per rank",
                                         "collective": "ncclReduceScatter(sum, fp32) on a second stream, two frames in flight"}
-    # (3) fused: the warp kernel adds its partial into the owners' slabs through peer memory
-    try:
-        ps = sharding.PeerSlabFusion(V, (Hb, Wb), C, frames=1, mode=wl.fusion, device=dev)
-        ms = timed(lambda: ps.run(f_r if ids else None, K_r, R_r, xd, yd, img))
-        sent = ps.bytes_over_nvlink_per_call()
-        t = torch.tensor([float(sent)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        out["peer_slab_fused"] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "nvlink_bytes_per_rank": int(t.item()),
-                                  "nvlink_gbs_per_rank": float(t.item()) / ms / 1e6, "result": f"{sharding.slab_rows(Hb, world)} BEV rows per rank",
-                                  "collective": "none: red.global.add.v4.f32 from the warp kernel into peer slabs (symmetric memory), "
-                                                "one cross-rank barrier per frame"}
-    except Exception as e:
-        out["peer_slab_fused"] = {"error": repr(e)[:300]}
+    # (3) fused: the warp kernel sends its partial sums into the owners' buffers through peer memory
+    for name, put, piped in (("peer_slab_add", False, False), ("peer_slab_put", True, False), ("peer_slab_put_overlapped", True, True)):
+        try:
+            ps = sharding.PeerSlabFusion(V, (Hb, Wb), C, frames=1, mode=wl.fusion, device=dev, put=put)
+            if piped:
+                tick = []
+
+                def ps_step():
+                    tick.append(ps.submit(f_r if ids else None, K_r, R_r, xd, yd, img))
+                    if len(tick) > 1:
+                        ps.wait(tick.pop(0))
+
+                def ps_drain():
+                    while tick:
+                        ps.wait(tick.pop(0))
+
+                ms = timed(ps_step, ps_drain)
+            else:
+                ms = timed(lambda: ps.run(f_r if ids else None, K_r, R_r, xd, yd, img))
+            sent = ps.bytes_over_nvlink_per_call()
+            t = torch.tensor([float(sent)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            how = ("cp.async.bulk stores from the warp kernel into this rank's receive buffer at each owner, owner-side ordered sum + division "
+                   "(bevipm_slab_finish)" if put else "cp.reduce.async.bulk add.f32 from the warp kernel into one slab per owner, owner zeroes it")
+            out[name] = {"ms_per_frame": ms, "frames_per_s": 1e3 / ms, "nvlink_bytes_per_rank": int(t.item()),
+                         "nvlink_gbs_per_rank": float(t.item()) / ms / 1e6, "result": f"{sharding.slab_rows(Hb, world)} BEV rows per rank",
+                         "collective": f"none: {how}; one cross-rank barrier per frame" + ("; the owner-side sum of frame t overlaps the warp of frame t+1" if piped else "")}
+            del ps
+        except Exception as e:
+            out[name] = {"error": repr(e)[:300]}
     out["nvlink_reference_gbs"] = {"peer_copy_per_direction": 770, "allreduce_bus_8_ranks": 725, "source": "B200_PROFILING.md"}
     return out
 

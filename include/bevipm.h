@@ -53,6 +53,9 @@ enum bevipm_mode { BEVIPM_SUM = 0, BEVIPM_MEAN = 1, BEVIPM_MAX = 2, BEVIPM_NONE 
  * read at p*size/(size-1) - 0.5; the caller passes BEV cell CORNERS x_min + j*res_x in xs/ys, which is where that
  * branch puts BEV pixel j).  From kornia's published algorithm; kornia is not installed here: parity unpinned. */
 #define BEVIPM_FLAG_KORNIA_GEOMETRY 1
+/* bevipm_warp_fuse_red only: store the partial sums instead of adding them (every rank owns a receive buffer at each
+ * owner; the owner sums them with bevipm_slab_finish): no atomics, no zeroing, reproducible sum order. */
+#define BEVIPM_FLAG_SLAB_PUT 2
 
 typedef struct bevipm_desc {
     int32_t B, V, C;        /* frames, views (cameras), channels */
@@ -141,9 +144,15 @@ int bevipm_divide_by_count(const bevipm_desc *d, float *bev, const int32_t *coun
  * strides d->os_b / os_y / os_x / os_c == 1 -- the rank's own memory or a peer's, mapped over NVLink (CUDA IPC, symmetric
  * memory).  16-byte red.global.add: the partial never lands in this rank's HBM.  Callers zero the slabs and barrier
  * across ranks before and after (bevipm/sharding.py: PeerSlabFusion).  d->mode must be BEVIPM_SUM, out_dtype f32.
+ * The sums leave the kernel as bulk copies from shared memory (cp.reduce.async.bulk add.f32, or plain cp.async.bulk stores
+ * with BEVIPM_FLAG_SLAB_PUT, when slabs[q] is THIS rank's private receive buffer at owner q).
  */
 int bevipm_warp_fuse_red(const bevipm_desc *d, const void *feats, const float *K, const float *Rt34, const float *xs,
                          const float *ys, void *const *slabs, int32_t nslabs, int32_t slab_rows, void *stream);
+
+/* Owner side of the PUT form: out[e] = (bufs[0][e] + ... + bufs[nbufs-1][e]) / divisor over n floats (n % 4 == 0), added in
+ * the order given, IEEE division; divisor 1 = plain sum. */
+int bevipm_slab_finish(const void *const *bufs, int32_t nbufs, float *out, int64_t n, float divisor, void *stream);
 
 /*
  * Phase-2 follow-on: multi-view, multi-head deformable-attention sampling (the slot the reference's

@@ -49,12 +49,18 @@ def _worker(rank, world, port, out_dir):
         slabs = [rs.wait(t) for t in tickets]
         assert all(torch.equal(slabs[0], s) for s in slabs[1:])
         res["reduce_scatter"] = slabs[0].cpu().numpy()
-        # (3) fused: partial sums added into the owners' slabs through peer memory
-        ps = sharding.PeerSlabFusion(V, bhw, C, frames=B, mode="mean", device=dev)
-        outs = [ps.run(f_r, K_r, R_r, xd, yd, img).clone() for _ in range(4)]   # both slab buffers, twice
+        # (3) fused: partial sums sent into the owners' buffers through peer memory: stores + owner-side sum, and adds
+        ps = sharding.PeerSlabFusion(V, bhw, C, frames=B, mode="mean", device=dev, put=True)
+        tickets = [ps.submit(f_r, K_r, R_r, xd, yd, img) for _ in range(5)]      # both buffer sets, pipelined
+        outs = [ps.wait(t).clone() for t in tickets]
         for o in outs[1:]:
-            assert torch.allclose(o, outs[0], rtol=1e-6, atol=1e-7)             # (atomics: the add order may differ run to run)
-        res["peer_slab"] = outs[0].cpu().numpy()
+            assert torch.equal(o, outs[0])                                       # stores + ordered sum: reproducible bit for bit
+        res["peer_slab_put"] = outs[0].cpu().numpy()
+        pa = sharding.PeerSlabFusion(V, bhw, C, frames=B, mode="mean", device=dev, put=False)
+        outs = [pa.run(f_r, K_r, R_r, xd, yd, img).clone() for _ in range(4)]
+        for o in outs[1:]:
+            assert torch.allclose(o, outs[0], rtol=1e-6, atol=1e-7)              # (reductions: the add order may differ run to run)
+        res["peer_slab_add"] = outs[0].cpu().numpy()
         res["nvlink_bytes"] = ps.bytes_over_nvlink_per_call()
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
@@ -82,7 +88,7 @@ def test_view_sharding_two_gpus(tmp_path):
         z = np.load(tmp_path / f"rank{rank}.npz")
         assert np.abs(z["allreduce"] - want).max() <= tol
         lo, hi = rank * rows, min(bhw[0], (rank + 1) * rows)
-        for name in ("reduce_scatter", "peer_slab"):
+        for name in ("reduce_scatter", "peer_slab_put", "peer_slab_add"):
             got = z[name][:, :, : hi - lo]
             assert got.shape == want[:, :, lo:hi].shape, name
             assert np.abs(got - want[:, :, lo:hi]).max() <= tol, name

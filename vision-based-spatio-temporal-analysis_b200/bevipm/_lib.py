@@ -13,6 +13,7 @@ LIB_PATH = Path(__import__("os").environ.get("BEVIPM_LIB", PKG / "libbevipm.so")
 
 F32, BF16 = 0, 1
 FLAG_KORNIA_GEOMETRY = 1
+FLAG_SLAB_PUT = 2
 SUM, MEAN, MAX, NONE = 0, 1, 2, 3
 MODES = {"sum": SUM, "mean": MEAN, "max": MAX, "none": NONE, "concat": NONE}
 
@@ -30,7 +31,7 @@ EXPORTS = (
     "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
     "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant", "bevipm_host_last_h2d_bytes",
-    "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red",
+    "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -67,12 +68,13 @@ def load() -> ctypes.CDLL:
     L.bevipm_valid_count.argtypes = [dp, fp, fp, fp, fp, vp, vp]
     L.bevipm_divide_by_count.argtypes = [dp, vp, vp, vp]
     L.bevipm_warp_fuse_red.argtypes = [dp, vp, fp, fp, fp, fp, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, ctypes.c_int32, vp]
+    L.bevipm_slab_finish.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int32, vp, ctypes.c_int64, ctypes.c_float, vp]
     L.bevipm_warp_fuse_host.argtypes = [dp, vp, fp, fp, fp, fp, vp]
     L.bevipm_host_release.restype = None
     L.bevipm_deform_attn_fwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, vp]
     L.bevipm_deform_attn_fwd.restype = ctypes.c_int
     for name in ("bevipm_warp_fuse_fwd", "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc",
-                 "bevipm_fuse_views", "bevipm_warp_fuse_host", "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red"):
+                 "bevipm_fuse_views", "bevipm_warp_fuse_host", "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish"):
         getattr(L, name).restype = ctypes.c_int
     _lib = L
     return L

@@ -168,62 +168,96 @@ class ReduceScatterFusion:
 
 
 class PeerSlabFusion:
-    """Fused compute + exchange: every rank's warp kernel adds its partial sum straight into the row slabs of their
-    owners through peer memory (bevipm_warp_fuse_red: red.global.add.v4.f32 on NVLink-mapped pointers from torch's
-    symmetric memory), so the partial BEV is never written to or re-read from local HBM and the transfer overlaps the
-    warp tile by tile.  Two slab buffers alternate, so zeroing the next one is off the critical path.
+    """Fused compute + exchange: every rank's warp kernel sends its partial sum straight to the owners of the BEV rows
+    through peer memory (bevipm_warp_fuse_red on NVLink-mapped pointers from torch's symmetric memory), as kilobyte bulk
+    copies out of shared memory, tile by tile while it warps: the partial BEV is never written to or re-read from local HBM.
 
-    run(feats_r, K_r, Rt_r, xs, ys, img_size) -> this rank's slab [B,C,rows,Wb] fp32 (valid until the call after next).
+      put=True  (default): every rank has a private receive buffer at each owner; the kernel STORES (cp.async.bulk), the
+                owner then adds the buffers in rank order and divides (bevipm_slab_finish, on a side stream so it overlaps
+                the next frame's warp).  No atomics, no zeroing, reproducible sums.
+      put=False: all ranks ADD into one slab per owner (cp.reduce.async.bulk add.f32); the owner zeroes it between uses.
+
+    Two buffer sets alternate; one cross-rank barrier per frame.
+    submit(...) -> ticket, wait(ticket) -> this rank's rows [B,C,rows,Wb] fp32; run(...) = wait(submit(...)).
     """
 
-    def __init__(self, views: int, bev_hw, channels: int, frames: int = 1, mode: str = "mean", group=None, device=None):
+    def __init__(self, views: int, bev_hw, channels: int, frames: int = 1, mode: str = "mean", group=None, device=None, put: bool = True):
         import torch.distributed._symmetric_memory as symm_mem
         if mode not in ("sum", "mean"):
             raise ValueError("peer-slab view sharding supports sum / mean")
-        self.views, self.mode = views, mode
+        self.views, self.mode, self.put = views, mode, put
         self.group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(self.group)
         self.rank = dist.get_rank(self.group)
         self.Hb, self.Wb = bev_hw
         self.C, self.B = channels, frames
         self.rows = slab_rows(self.Hb, self.world)
-        self.buf = symm_mem.empty((2, frames, self.rows, self.Wb, channels), dtype=torch.float32, device=device)
+        self.slab_elems = frames * self.rows * self.Wb * channels
+        self.nsrc = self.world if put else 1
+        self.sources = [r for r, ids in enumerate(view_assignment(views, self.world)) if ids]   # ranks that hold cameras
+        self.buf = symm_mem.empty((2, self.nsrc, frames, self.rows, self.Wb, channels), dtype=torch.float32, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
         self.buf.zero_()
         self.turn = 0
+        self.side = torch.cuda.Stream(device=device)
+        self._last_finish = None
         self._div = torch.tensor(float(views), device=device)
         self.hdl.barrier()
 
     def bytes_over_nvlink_per_call(self) -> int:
-        """fp32 bytes this rank adds into OTHER ranks' slabs per call (what crosses NVLink)."""
+        """fp32 bytes this rank sends into OTHER ranks' buffers per call (what crosses NVLink)."""
         own = min(self.rows, max(0, self.Hb - self.rank * self.rows))
         return self.B * (self.Hb - own) * self.Wb * self.C * 4
 
-    def run(self, feats_r, K_r, Rt_r, xs, ys, img_size):
+    def submit(self, feats_r, K_r, Rt_r, xs, ys, img_size):
         import ctypes
         from . import _lib, ops
         k = self.turn
         self.turn ^= 1
-        slab = self.buf[k]
-        stream = torch.cuda.current_stream()
-        # Slab k was zeroed by its owner right after its previous use, two calls ago (or at construction): the closing
-        # barrier of the call in between already ordered every rank's zeroing before any rank's adds of this call.
+        main = torch.cuda.current_stream()
+        L = _lib.load()
+        # Buffer set k was last read (put: by the owners' finish kernels; add: zeroed) two calls ago: the barrier of the call
+        # in between ordered that before any rank's writes of this call.
         if feats_r is not None and feats_r.shape[1] > 0:
-            B, V, C, Hf, Wf = feats_r.shape
             if not ops._is_channels_last5(feats_r):
                 raise ValueError("PeerSlabFusion wants channels-last features")
             d = ops._fill_desc(feats_r.shape, feats_r.stride(), (self.rows * self.Wb * self.C, 0, 1, self.Wb * self.C, self.C),
-                               (self.Hb, self.Wb), (int(img_size[0]), int(img_size[1])), _lib.SUM, ops._DT[feats_r.dtype], _lib.F32, 0)
-            off = k * self.B * self.rows * self.Wb * self.C * 4
+                               (self.Hb, self.Wb), (int(img_size[0]), int(img_size[1])), _lib.SUM, ops._DT[feats_r.dtype], _lib.F32, 0,
+                               _lib.FLAG_SLAB_PUT if self.put else 0)
+            off = ((k * self.nsrc + (self.rank if self.put else 0)) * self.slab_elems) * 4
             arr = (ctypes.c_void_p * self.world)(*[p + off for p in self.ptrs])
-            _lib.check(_lib.load().bevipm_warp_fuse_red(ctypes.byref(d), ops._ptr(feats_r), ops._ptr(K_r), ops._ptr(Rt_r), ops._ptr(xs),
-                                                        ops._ptr(ys), arr, self.world, self.rows, ctypes.c_void_p(stream.cuda_stream)))
-        self.hdl.barrier()                                    # every rank's adds have landed in my slab
-        out = slab.permute(0, 3, 1, 2)                        # logical [B,C,rows,Wb]
-        if self.mode == "mean":
-            out = out / self._div                             # IEEE division by V on the owner's rows (fusion.py:20-21)
-        else:
-            out = out.clone()
-        slab.zero_()                                          # ready for its next turn (two calls from now)
+            _lib.check(L.bevipm_warp_fuse_red(ctypes.byref(d), ops._ptr(feats_r), ops._ptr(K_r), ops._ptr(Rt_r), ops._ptr(xs),
+                                              ops._ptr(ys), arr, self.world, self.rows, ctypes.c_void_p(main.cuda_stream)))
+        if self._last_finish is not None:
+            main.wait_event(self._last_finish)                # my previous finish has read its buffers before others may pass on
+        self.hdl.barrier()                                    # every rank's partial sums for this frame have landed
+        if not self.put:
+            slab = self.buf[k, 0]
+            out = slab.permute(0, 3, 1, 2)
+            out = out / self._div if self.mode == "mean" else out.clone()
+            slab.zero_()                                      # ready for its next turn (two calls from now)
+            return out, None
+        landed = torch.cuda.Event()
+        landed.record(main)
+        out = torch.empty((self.B, self.rows, self.Wb, self.C), device=self.buf.device, dtype=torch.float32)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(landed)
+            base = self.buf.data_ptr() + k * self.nsrc * self.slab_elems * 4
+            arr = (ctypes.c_void_p * len(self.sources))(*[base + r * self.slab_elems * 4 for r in self.sources])
+            _lib.check(L.bevipm_slab_finish(arr, len(self.sources), ops._ptr(out), self.slab_elems,
+                                            float(self.views) if self.mode == "mean" else 1.0, ctypes.c_void_p(self.side.cuda_stream)))
+            done = torch.cuda.Event()
+            done.record(self.side)
+        out.record_stream(self.side)
+        self._last_finish = done
+        return out.permute(0, 3, 1, 2), done                  # logical [B,C,rows,Wb]
+
+    def wait(self, ticket) -> torch.Tensor:
+        out, done = ticket
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
         return out
+
+    def run(self, feats_r, K_r, Rt_r, xs, ys, img_size):
+        return self.wait(self.submit(feats_r, K_r, Rt_r, xs, ys, img_size))

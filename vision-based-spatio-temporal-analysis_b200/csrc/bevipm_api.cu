@@ -73,6 +73,7 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
     p.kx = p.ky = 0.0f;
     for (int q = 0; q < 16; ++q) p.slab[q] = nullptr;
     p.slab_rows = 1;
+    p.slab_put = 0;
     if (d->flags & BEVIPM_FLAG_KORNIA_GEOMETRY) {
         p.kx = d->Wf > 1 ? (float)((double)d->Wf / (double)(d->Wf - 1)) : 1.0f;
         p.ky = d->Hf > 1 ? (float)((double)d->Hf / (double)(d->Hf - 1)) : 1.0f;

@@ -15,6 +15,11 @@ int set_error(int code, const char* msg);
 FwdParams params_from_desc(const bevipm_desc* d, const void* feats, const float* K, const float* Rt, const float* xs, const float* ys, void* out);
 int check_desc_public(const bevipm_desc* d);
 
+struct FinishArgs {
+    const float* buf[16];
+    int n;
+};
+
 namespace {
 template <typename TIn, int MAXREG>
 int launch_red(FwdParams p, cudaStream_t st) {
@@ -42,6 +47,39 @@ int launch_red(FwdParams p, cudaStream_t st) {
 }  // namespace
 }  // namespace bevipm
 
+namespace bevipm {
+// out[e] = (bufs[0][e] + bufs[1][e] + ...) / divisor, added in the order given (rank order: the result is reproducible),
+// IEEE division (fusion.py:20-21); divisor 1 leaves the sum.
+__global__ void __launch_bounds__(256) slab_finish_kernel(FinishArgs a, float* __restrict__ out, long long n4, float divisor) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n4; e += (long long)gridDim.x * blockDim.x) {
+        float4 s = __ldcs(reinterpret_cast<const float4*>(a.buf[0]) + e);
+        for (int q = 1; q < a.n; ++q) {
+            const float4 t = __ldcs(reinterpret_cast<const float4*>(a.buf[q]) + e);
+            s.x = __fadd_rn(s.x, t.x); s.y = __fadd_rn(s.y, t.y); s.z = __fadd_rn(s.z, t.z); s.w = __fadd_rn(s.w, t.w);
+        }
+        if (divisor != 1.0f) { s.x = __fdiv_rn(s.x, divisor); s.y = __fdiv_rn(s.y, divisor); s.z = __fdiv_rn(s.z, divisor); s.w = __fdiv_rn(s.w, divisor); }
+        reinterpret_cast<float4*>(out)[e] = s;
+    }
+}
+}  // namespace bevipm
+
+extern "C" int bevipm_slab_finish(const void* const* bufs, int32_t nbufs, float* out, int64_t n, float divisor, void* stream) {
+    using namespace bevipm;
+    if (!bufs || !out || nbufs < 1 || nbufs > 16 || n <= 0 || (n & 3)) return set_error(BEVIPM_ERR_BAD_ARG, "slab_finish: 1..16 buffers of n (multiple of 4) floats");
+    FinishArgs a;
+    a.n = nbufs;
+    for (int q = 0; q < nbufs; ++q) {
+        if (!bufs[q] || (reinterpret_cast<uintptr_t>(bufs[q]) & 15)) return set_error(BEVIPM_ERR_BAD_ARG, "slab_finish: buffers must be 16-byte aligned");
+        a.buf[q] = static_cast<const float*>(bufs[q]);
+    }
+    const long long n4 = n / 4;
+    const long long want = (n4 + 255) / 256;
+    slab_finish_kernel<<<(unsigned)std::min<long long>(want, 148LL * 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(a, out, n4, divisor);
+    if (cudaGetLastError() != cudaSuccess) return set_error(BEVIPM_ERR_CUDA, "slab_finish launch failed");
+    note_launch(61);
+    return 0;
+}
+
 extern "C" int bevipm_warp_fuse_red(const bevipm_desc* d, const void* feats, const float* K, const float* Rt34, const float* xs,
                                     const float* ys, void* const* slabs, int32_t nslabs, int32_t slab_rows, void* stream) {
     using namespace bevipm;
@@ -64,6 +102,7 @@ extern "C" int bevipm_warp_fuse_red(const bevipm_desc* d, const void* feats, con
         p.slab[q] = slabs[q];
     }
     p.slab_rows = slab_rows;
+    p.slab_put = (d->flags & BEVIPM_FLAG_SLAB_PUT) ? 1 : 0;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return d->in_dtype == BEVIPM_F32 ? launch_red<float, 96>(p, st) : launch_red<__nv_bfloat16, 128>(p, st);
 }

@@ -50,6 +50,7 @@ struct FwdParams {
     // fp32 buffer of the rank that owns them (its own memory or a peer's, mapped over NVLink); strides os_* are a slab's
     void* slab[16];
     int slab_rows;
+    int slab_put;        // 0: add into the slab (bulk reduction); 1: plain bulk store (every rank has its own receive buffer at the owner)
 };
 
 enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2, KM_PROBE = 3 /* timing probe: loads only, no blend */,

@@ -605,11 +605,14 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                     const int ch = min(32 * VE, p.C - k_this * 32 * VE);       // channels of this chunk that exist
                     const int ncell = min(CELLS, p.Wb - j0);
                     const uint32_t src = (uint32_t)__cvta_generic_to_shared(stg);
-                    if (ch * 4 == CB && p.os_x == 32 * VE) {                      // one chunk per texel: the cells are contiguous
-                        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(oc), "r"(src), "r"(ncell * CB) : "memory");
+                    const bool run = ch * 4 == CB && p.os_x == 32 * VE;          // one chunk per texel: the cells are contiguous
+                    const int nop = run ? 1 : ncell, sz = run ? ncell * CB : ch * 4;
+                    if (p.slab_put) {   // this rank's own receive buffer at the owner: plain stores, summed by the owner afterwards
+                        for (int c = 0; c < nop; ++c)
+                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(oc + (long long)c * p.os_x), "r"(src + c * CB), "r"(sz) : "memory");
                     } else {
-                        for (int c = 0; c < ncell; ++c)
-                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(oc + (long long)c * p.os_x), "r"(src + c * CB), "r"(ch * 4) : "memory");
+                        for (int c = 0; c < nop; ++c)
+                            asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(oc + (long long)c * p.os_x), "r"(src + c * CB), "r"(sz) : "memory");
                     }
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
