@@ -62,6 +62,13 @@ def _worker(rank, world, port, out_dir):
             assert torch.allclose(o, outs[0], rtol=1e-6, atol=1e-7)              # (reductions: the add order may differ run to run)
         res["peer_slab_add"] = outs[0].cpu().numpy()
         res["nvlink_bytes"] = ps.bytes_over_nvlink_per_call()
+        # (4) the same exchange on the copy engines (DMA peer copies on a second stream)
+        ce = sharding.CopyEngineSlabFusion(V, bhw, C, frames=B, mode="mean", device=dev)
+        tickets = [ce.submit(ops.warp_fuse(f_r, K_r, R_r, xd, yd, img[0], img[1], _lib.SUM, False, 0)) for _ in range(5)]
+        outs = [ce.wait(t).clone() for t in tickets]
+        for o in outs:
+            assert torch.equal(o, torch.from_numpy(res["peer_slab_put"]).to(dev))   # same ordered sum, bit for bit
+        res["copy_engine"] = outs[0].cpu().numpy()
         torch.cuda.synchronize()
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), **res)
     finally:
@@ -88,7 +95,7 @@ def test_view_sharding_two_gpus(tmp_path):
         z = np.load(tmp_path / f"rank{rank}.npz")
         assert np.abs(z["allreduce"] - want).max() <= tol
         lo, hi = rank * rows, min(bhw[0], (rank + 1) * rows)
-        for name in ("reduce_scatter", "peer_slab_put", "peer_slab_add"):
+        for name in ("reduce_scatter", "peer_slab_put", "peer_slab_add", "copy_engine"):
             got = z[name][:, :, : hi - lo]
             assert got.shape == want[:, :, lo:hi].shape, name
             assert np.abs(got - want[:, :, lo:hi]).max() <= tol, name

@@ -261,3 +261,79 @@ class PeerSlabFusion:
 
     def run(self, feats_r, K_r, Rt_r, xs, ys, img_size):
         return self.wait(self.submit(feats_r, K_r, Rt_r, xs, ys, img_size))
+
+
+class CopyEngineSlabFusion:
+    """Row-slab view sharding with the exchange on the copy engines: the ordinary fused SUM kernel writes this rank's
+    partial BEV to local HBM, DMA copies (peer-to-peer over NVLink, a second stream) push every other owner's rows into
+    this rank's receive buffer there, one cross-rank barrier, and the owner adds the buffers in rank order and divides
+    (bevipm_slab_finish).  Copies and owner-side sums of frame t overlap the warp of frame t+1; nothing but the warp kernel
+    runs on the SMs of the compute stream.  Same results as PeerSlabFusion(put=True), bit for bit.
+
+    submit(part) -> ticket with part = this rank's partial sum [B,C,Hb,Wb] fp32 channels-last (ops.warp_fuse, mode SUM) or
+    None for a rank without cameras; wait(ticket) -> this rank's rows [B,C,rows,Wb].
+    """
+
+    def __init__(self, views: int, bev_hw, channels: int, frames: int = 1, mode: str = "mean", group=None, device=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        if mode not in ("sum", "mean"):
+            raise ValueError("copy-engine view sharding supports sum / mean")
+        self.views, self.mode = views, mode
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.Hb, self.Wb = bev_hw
+        self.C, self.B = channels, frames
+        self.rows = slab_rows(self.Hb, self.world)
+        if frames != 1 and self.rows * self.world != self.Hb:
+            raise ValueError("several frames per call need bev_h divisible by the number of ranks")
+        self.slab_elems = frames * self.rows * self.Wb * channels
+        self.sources = [r for r, ids in enumerate(view_assignment(views, self.world)) if ids]
+        self.buf = symm_mem.empty((2, self.world, frames, self.rows, self.Wb, channels), dtype=torch.float32, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.buf.zero_()
+        # peer views of MY receive slot at every owner, both buffer sets
+        self.peer = [[self.hdl.get_buffer(q, (frames, self.rows, self.Wb, channels), torch.float32,
+                                          (k * self.world + self.rank) * self.slab_elems) for q in range(self.world)] for k in range(2)]
+        self.turn = 0
+        self.side = torch.cuda.Stream(device=device)
+        self._last_finish = None
+        self.hdl.barrier()
+
+    def bytes_over_nvlink_per_call(self) -> int:
+        own = min(self.rows, max(0, self.Hb - self.rank * self.rows))
+        return self.B * (self.Hb - own) * self.Wb * self.C * 4
+
+    def submit(self, part):
+        import ctypes
+        from . import _lib, ops
+        k = self.turn
+        self.turn ^= 1
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        out = torch.empty((self.B, self.rows, self.Wb, self.C), device=self.buf.device, dtype=torch.float32)
+        with torch.cuda.stream(self.side):
+            self.side.wait_event(ready)
+            if part is not None:
+                mem = part.permute(0, 2, 3, 1)                 # [B,Hb,Wb,C] as it lies in memory
+                for q in range(self.world):
+                    lo, hi = q * self.rows, min(self.Hb, (q + 1) * self.rows)
+                    if hi > lo:                                # (my own rows go through my own slot too: one code path)
+                        self.peer[k][q][:, : hi - lo].copy_(mem[:, lo:hi], non_blocking=True)
+                part.record_stream(self.side)
+            self.hdl.barrier()                                 # every rank's copies for this frame have landed
+            base = self.buf.data_ptr() + k * self.world * self.slab_elems * 4
+            arr = (ctypes.c_void_p * len(self.sources))(*[base + r * self.slab_elems * 4 for r in self.sources])
+            _lib.check(_lib.load().bevipm_slab_finish(arr, len(self.sources), ops._ptr(out), self.slab_elems,
+                                                      float(self.views) if self.mode == "mean" else 1.0,
+                                                      ctypes.c_void_p(self.side.cuda_stream)))
+            done = torch.cuda.Event()
+            done.record(self.side)
+        out.record_stream(self.side)
+        return out.permute(0, 3, 1, 2), done
+
+    def wait(self, ticket) -> torch.Tensor:
+        out, done = ticket
+        torch.cuda.current_stream().wait_event(done)
+        return out
