@@ -15,7 +15,7 @@ from test_gpu_parity import DEV, _bcast, _rig_case, _run, _same
 
 pytestmark = pytest.mark.gpu
 
-STAGED = [50, 51]   # 8-row tiles (2 CTAs / SM), 4-row tiles (4 CTAs / SM)
+STAGED = [50, 51, 55]   # staged tiles: 8-row (2 CTAs / SM), 4-row (4 CTAs / SM); 55: run kernel with the TMA-box ring
 
 
 @pytest.mark.parametrize("variant", STAGED)

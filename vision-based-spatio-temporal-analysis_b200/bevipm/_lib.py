@@ -100,6 +100,8 @@ def variant_name(v: int) -> str:
         return f"warp_fuse_list_kernel (variant {v})"
     if 30 <= v <= 41:
         return f"warp_fuse_run_kernel (variant {v})"
+    if v == 55:
+        return "warp_fuse_boxrun_kernel (run kernel, ring filled by TMA 2x2 box copies, variant 55)"
     if v == 60:
         return "warp_fuse_run_kernel<KM_RED> (partial sums added into peer slabs)"
     if 50 <= v <= 53:

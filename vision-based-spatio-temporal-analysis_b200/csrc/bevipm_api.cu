@@ -86,7 +86,7 @@ int ceil_div(int a, int b) { return (a + b - 1) / b; }
 // ---- fused NHWC fast path ---------------------------------------------------------------------
 // variant ids (bevipm_desc.variant); 0 = auto.  1..10 tile kernel shapes, 11..14 its loads-only timing probes,
 // 20..27 list kernel shapes, 30..39 run kernel shapes, 40 / 41 its timing probes: see dispatch_fused.
-constexpr int kNumVariants = 54;  // 50 / 51: TMA-staged kernel (8- / 4-row tiles), 52 / 53: its timing probes (no copies / no blend)
+constexpr int kNumVariants = 56;  // 55: run kernel with the TMA-box ring;  // 50 / 51: TMA-staged kernel (8- / 4-row tiles), 52 / 53: its timing probes (no copies / no blend)
 constexpr int kTH = 8;
 
 template <typename TIn, typename TOut, int NV, int CELLS, int KMODE, int MINB, bool PIPE>
@@ -189,6 +189,11 @@ int launch_staged_variant(const FwdParams& p, int variant, cudaStream_t st) {
 template <typename TIn, typename TOut>
 int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     if (variant >= 50 && variant <= 53) return launch_staged_variant<TIn, TOut>(p, variant, st);
+    if (variant == 55) {
+        const int rc = bevipm::launch_boxrun(p, sizeof(TIn) == 2, sizeof(TOut) == 2, st, g_err, sizeof(g_err));
+        if (rc == 0) { g_last_variant = 55; g_launches.fetch_add(1, std::memory_order_relaxed); }
+        return rc;
+    }
     if (p.mode == BEVIPM_MAX) {
         // max fusion (fusion.py:22): the list kernel's KM_MAX walk (2.5x the tile kernel on config 1); the tile kernel
         // when the caller forces it (variant 1) or the maps are too large for 32-bit tap offsets

@@ -11,9 +11,11 @@
 
 #include "../../include/bevipm.h"
 #include "ipm_staged.cuh"
+#include "ipm_boxrun.cuh"
 #include "staged_api.h"
 
 namespace bevipm {
+bool staged_supported(const FwdParams& p, bool in_bf16);
 namespace {
 
 int st_fail(char* err, size_t n, int code, const char* fmt, ...) {
@@ -151,7 +153,50 @@ int launch_mode(const FwdParams& p, int cps, int probe, cudaStream_t st, char* e
     return launch_t<TIn, TOut, NW, KM_ACC, 0>(p, cps, st, err, errlen);
 }
 
+// ---- run kernel with the TMA-box ring (ipm_boxrun.cuh) ----------------------------------------------------------------
+template <typename TIn, typename TOut, int MAXREG, int KMODE>
+int launch_box_t(FwdParams p, cudaStream_t st, char* err, size_t errlen) {
+    constexpr int VE = VecTraits<TIn>::VE, CELLS = 8, NW = 4, DEPTH = 4;
+    p.tiles_x = (p.Wb + CELLS - 1) / CELLS;
+    p.tiles_y = (p.Hb + NW - 1) / NW;
+    p.fsy16 = (int)(p.fs_y / VE);
+    p.fsx16 = (int)(p.fs_x / VE);
+    p.rcpV = 1.0f / (float)p.V;
+    auto kern = warp_fuse_boxrun_kernel<TIn, TOut, CELLS, NW, MAXREG, DEPTH, KMODE>;
+    const size_t smem = (size_t)run_tables_bytes(p.V, CELLS, NW) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return st_fail(err, errlen, BEVIPM_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+    }
+    int fpc = 1;
+    {
+        const long long tiles = (long long)p.tiles_x * p.tiles_y, slots = 148LL * (65536 / (MAXREG * 32 * NW));
+        while (fpc < 8 && fpc * 2 <= p.B && tiles * ((p.B + fpc * 2 - 1) / (fpc * 2)) >= 16 * slots) fpc *= 2;
+        fpc = std::max(1, std::min(env_int("BEVIPM_RUN_FPC", fpc), p.B));
+    }
+    dim3 grid(p.tiles_x * p.tiles_y, 1, (p.B + fpc - 1) / fpc);
+    kern<<<grid, NW * 32, smem, st>>>(p, fpc, g_maps.m[kStBlockMap]);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return st_fail(err, errlen, BEVIPM_ERR_CUDA, "box-ring kernel launch: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+template <typename TIn, typename TOut, int MAXREG>
+int launch_box_mode(const FwdParams& p, cudaStream_t st, char* err, size_t errlen) {
+    if (p.mode == BEVIPM_MAX) return launch_box_t<TIn, TOut, MAXREG, KM_MAX>(p, st, err, errlen);
+    return launch_box_t<TIn, TOut, MAXREG, KM_ACC>(p, st, err, errlen);
+}
+
 }  // namespace
+
+int launch_boxrun(FwdParams p, bool in_bf16, bool out_bf16, cudaStream_t st, char* err, size_t errlen) {
+    if (!staged_supported(p, in_bf16)) return st_fail(err, errlen, BEVIPM_ERR_UNSUPPORTED, "box-ring kernel: strides / extents / mode not supported");
+    if (int rc = build_maps(p, in_bf16, err, errlen)) return rc;
+    if (!in_bf16 && !out_bf16) return launch_box_mode<float, float, 96>(p, st, err, errlen);
+    if (in_bf16 && out_bf16) return launch_box_mode<__nv_bfloat16, __nv_bfloat16, 128>(p, st, err, errlen);
+    if (in_bf16 && !out_bf16) return launch_box_mode<__nv_bfloat16, float, 128>(p, st, err, errlen);
+    return st_fail(err, errlen, BEVIPM_ERR_UNSUPPORTED, "box-ring kernel: fp32 features with bf16 output are not built");
+}
 
 bool staged_supported(const FwdParams& p, bool in_bf16) {
     const long long es = in_bf16 ? 2 : 4;

@@ -110,7 +110,9 @@ __device__ __forceinline__ void run_copy_entry(uint32_t stage, unsigned long lon
 // HALF: a reload whose block is the previous one shifted by exactly one texel in x (both blocks fully inside the map)
 // becomes a HALF entry: only the new column's two taps are listed ({top, bottom, -2, 0}), the walk keeps the other
 // column in registers; per view, ml[2V+3+v] = half bits | (moved-to-the-east bits << 16).
-template <int CELLS, bool WANT_ALL_SEEN, bool MARK_INVALID, bool HALF = false>
+// BOX: the load list holds texel coordinates instead of tap offsets ({x0 | y0 << 16, view, -, -}; end of list: view -1),
+// for rings that are filled by one tensor-map [2 x 2] box copy per reload (ipm_boxrun.cuh).
+template <int CELLS, bool WANT_ALL_SEEN, bool MARK_INVALID, bool HALF = false, bool BOX = false>
 __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int i, int j0, int lane, int fsv16, const float* sH,
                                                  float4* wts, int4* loads, int* ml) {
     constexpr int GPW = 32 / CELLS;
@@ -175,6 +177,7 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
             if (reload) {
                 int4 entry = make_int4(off[0], off[1], off[2], off[3]);
                 if (HALF && half) entry = east ? make_int4(off[1], off[3], -2, 0) : make_int4(off[0], off[2], -2, 0);  // the new column
+                if (BOX) entry = make_int4((t.x0 & 0xffff) | (t.y0 << 16), v, 0, 0);
                 loads[nloads + __popc(reload_b & lt)] = entry;
             }
             if (c == 0) {
@@ -192,7 +195,7 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
         }
     }
     if (lane == 0) { ml[2 * V] = nseen; ml[2 * V + 1] = nloads; ml[2 * V + 2] = (int)all_seen; }
-    if (lane < 8) loads[nloads + lane] = make_int4(-1, 0, 0, 0);  // end of list
+    if (lane < 8) loads[nloads + lane] = make_int4(-1, -1, 0, 0);  // end of list
 }
 
 // ---- TMA form of the ring (template flag TMA): one elected lane hands the copy engine four 512-byte bulk copies per

@@ -13,6 +13,9 @@ namespace bevipm {
 // staged kernel: the caller falls back to the run kernel when the variant was not forced).
 int launch_staged(FwdParams p, bool in_bf16, bool out_bf16, int shape, int probe, cudaStream_t st, char* err, size_t errlen);
 
+// The run kernel with its ring filled by one tensor-map [2 x 2] box copy per reload (ipm_boxrun.cuh); sum / mean / max.
+int launch_boxrun(FwdParams p, bool in_bf16, bool out_bf16, cudaStream_t st, char* err, size_t errlen);
+
 // Can the staged kernel take this launch at all (TMA stride rules, map sizes, fusion mode)?
 bool staged_supported(const FwdParams& p, bool in_bf16);
 
