@@ -172,6 +172,12 @@ int bevipm_deform_attn_fwd(const bevipm_deform_desc *d, const void *value, const
                            const int64_t *level_start, const float *loc, const float *attn, void *out,
                            void *stream);
 
+/* Backward of bevipm_deform_attn_fwd: grad_value [B,S,M,D] f32 (PRE-ZEROED by the caller, accumulated with atomics), grad_loc
+ * [B,Q,M,L,P,2] f32 and grad_attn [B,Q,M,L,P] f32 from grad_out [B,Q,M*D] (d->out_dtype).  Any of the three may be null. */
+int bevipm_deform_attn_bwd(const bevipm_deform_desc *d, const void *value, const int32_t *shapes,
+                           const int64_t *level_start, const float *loc, const float *attn, const void *grad_out,
+                           float *grad_value, float *grad_loc, float *grad_attn, void *stream);
+
 /*
  * Host-buffer entry (the call a non-torch integrator makes, and what bench.py's e2e times):
  * feats/out are HOST pointers (pinned for full PCIe rate) laid out as feats [B,V,Hf,Wf,C] and

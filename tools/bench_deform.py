@@ -39,10 +39,37 @@ def main():
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     nbytes = values[0].numel() * 2 + loc.numel() * 4 + aw.numel() * 4 + B * Q * M * D * 2
+    # forward + backward (grad value fp32 zero-fill + atomics, grad loc, grad attn) minus forward
+    vg = [v.clone().requires_grad_(True) for v in values]
+    lg, ag = loc.clone().requires_grad_(True), aw.clone().requires_grad_(True)
+    cot = torch.randn(B, Q, M * D, device="cuda", generator=g).bfloat16()
+
+    def fb(i):
+        out = ops.deform_attn(vg[i % nbuf], shapes, start, lg, ag)
+        out.backward(cot)
+        vg[i % nbuf].grad = None
+        lg.grad = None
+        ag.grad = None
+
+    for i in range(3):
+        fb(i)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(30):
+        fb(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_fb = e0.elapsed_time(e1) / 30
+    peak = 6543.1
+    try:
+        peak = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["hbm_gbs"])
+    except Exception:
+        pass
     print(json.dumps({"workload": "c4 deformable attention 120x360 queries, 8 heads x 4 pts x 7 views, 256 ch bf16",
                       "ms": ms, "frames_per_s": B / (ms * 1e-3), "bytes_full_per_frame": nbytes,
-                      "gbs_full": nbytes / (ms * 1e-3) / 1e9,
-                      "tap_bytes_through_l1": B * Q * M * L * P * 4 * D * 2}))
+                      "gbs_full": nbytes / (ms * 1e-3) / 1e9, "roofline_frac_of_measured_hbm": nbytes / (ms * 1e-3) / 1e9 / peak,
+                      "tap_bytes_through_l1": B * Q * M * L * P * 4 * D * 2,
+                      "forward_plus_backward_ms": ms_fb, "backward_ms": ms_fb - ms}))
 
 
 if __name__ == "__main__":

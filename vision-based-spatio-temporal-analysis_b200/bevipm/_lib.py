@@ -31,7 +31,7 @@ EXPORTS = (
     "bevipm_version", "bevipm_last_error", "bevipm_launch_count", "bevipm_warp_fuse_fwd",
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
     "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant", "bevipm_host_last_h2d_bytes",
-    "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish",
+    "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish", "bevipm_deform_attn_bwd",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -73,6 +73,8 @@ def load() -> ctypes.CDLL:
     L.bevipm_host_release.restype = None
     L.bevipm_deform_attn_fwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, vp]
     L.bevipm_deform_attn_fwd.restype = ctypes.c_int
+    L.bevipm_deform_attn_bwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, fp, fp, fp, vp]
+    L.bevipm_deform_attn_bwd.restype = ctypes.c_int
     for name in ("bevipm_warp_fuse_fwd", "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc",
                  "bevipm_fuse_views", "bevipm_warp_fuse_host", "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish"):
         getattr(L, name).restype = ctypes.c_int

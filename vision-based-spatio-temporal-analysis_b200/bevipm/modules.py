@@ -390,7 +390,7 @@ class DeformAttnFusion(FusionModule):
 
     forward(bev_maps [B,V,C,H,W]) -> [B,C,H,W].  The projections are ordinary nn.Linear layers; the
     sampling itself (B*H*W*heads*V*points bilinear gathers) runs in `bevipm_deform_attn_fwd`.
-    Forward only: use it for inference, or fine-tune the projections with the sampling detached.
+    Trainable end to end: the sampling's backward (d value, d locations, d weights) runs in `bevipm_deform_attn_bwd`.
     """
 
     def __init__(self, channels: int, views: int, heads: int = 8, points: int = 4):
@@ -414,7 +414,6 @@ class DeformAttnFusion(FusionModule):
         nn.init.zeros_(self.attention_weights.weight)
         nn.init.zeros_(self.attention_weights.bias)
 
-    @torch.no_grad()
     def forward(self, bev_maps: torch.Tensor) -> torch.Tensor:
         B, V, C, H, W = bev_maps.shape
         assert V == self.views and C == self.channels

@@ -328,13 +328,57 @@ def warp_fuse_host(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs:
 
 # ---- Phase-2 follow-on: deformable-attention sampling ---------------------------------------------------
 
+def _deform_fwd(value, shp, start, loc, aw, out_dtype):
+    B, S, M, D = value.shape
+    _, Q, _, Lv, P, _ = loc.shape
+    dev = value.device
+    out = torch.empty((B, Q, M * D), device=dev, dtype=out_dtype)
+    d = _lib.DeformDesc()
+    d.B, d.Q, d.M, d.D, d.L, d.P = B, Q, M, D, Lv, P
+    d.value_dtype, d.out_dtype, d.S = _DT[value.dtype], _DT[out_dtype], S
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bevipm_deform_attn_fwd(ctypes.byref(d), _ptr(value), _ptr(shp), _ptr(start), _ptr(loc), _ptr(aw),
+                                                      _ptr(out), ctypes.c_void_p(_stream_ptr(dev))))
+    return out
+
+
+class _DeformAttn(torch.autograd.Function):
+    """Forward and backward of the sampling in libbevipm.so (bevipm_deform_attn_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, value, shp, start, loc, aw, out_dtype):
+        ctx.save_for_backward(value, shp, start, loc, aw)
+        ctx.out_dtype = out_dtype
+        return _deform_fwd(value, shp, start, loc, aw, out_dtype)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        value, shp, start, loc, aw = ctx.saved_tensors
+        B, S, M, D = value.shape
+        _, Q, _, Lv, P, _ = loc.shape
+        dev = value.device
+        g = grad_out.contiguous()
+        if g.dtype not in _DT:
+            g = g.float()
+        gv = torch.zeros((B, S, M, D), device=dev, dtype=torch.float32)
+        gl = torch.empty(loc.shape, device=dev, dtype=torch.float32)
+        ga = torch.empty(aw.shape, device=dev, dtype=torch.float32)
+        d = _lib.DeformDesc()
+        d.B, d.Q, d.M, d.D, d.L, d.P = B, Q, M, D, Lv, P
+        d.value_dtype, d.out_dtype, d.S = _DT[value.dtype], _DT[g.dtype], S
+        with torch.cuda.device(dev):
+            _lib.check(_lib.load().bevipm_deform_attn_bwd(ctypes.byref(d), _ptr(value), _ptr(shp), _ptr(start), _ptr(loc), _ptr(aw), _ptr(g),
+                                                          _ptr(gv), _ptr(gl), _ptr(ga), ctypes.c_void_p(_stream_ptr(dev))))
+        return gv.to(value.dtype), None, None, gl, ga, None
+
+
 def deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_index: torch.Tensor,
                 sampling_locations: torch.Tensor, attention_weights: torch.Tensor, out_dtype=None) -> torch.Tensor:
-    """MSDeformAttn forward (Deformable-DETR semantics, one level per camera view).
+    """MSDeformAttn (Deformable-DETR semantics, one level per camera view), forward and backward on our kernels.
 
     value [B,S,M,D] float32/bfloat16, spatial_shapes [L,2] (H,W), level_start_index [L],
     sampling_locations [B,Q,M,L,P,2] in [0,1], attention_weights [B,Q,M,L,P]  ->  [B,Q,M*D].
-    Forward only (inference fusion); CUDA tensors only.
+    Differentiable w.r.t. value, sampling_locations and attention_weights; CUDA tensors only.
     """
     if not value.is_cuda:
         raise RuntimeError("bevipm runs on CUDA tensors only: there is no CPU implementation of this path")
@@ -353,11 +397,6 @@ def deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_i
     shp = spatial_shapes.to(device=dev, dtype=torch.int32).contiguous()
     start = level_start_index.to(device=dev, dtype=torch.int64).contiguous()
     out_dtype = out_dtype or value.dtype
-    out = torch.empty((B, Q, M * D), device=dev, dtype=out_dtype)
-    d = _lib.DeformDesc()
-    d.B, d.Q, d.M, d.D, d.L, d.P = B, Q, M, D, Lv, P
-    d.value_dtype, d.out_dtype, d.S = _DT[value.dtype], _DT[out_dtype], S
-    with torch.cuda.device(dev):
-        _lib.check(_lib.load().bevipm_deform_attn_fwd(ctypes.byref(d), _ptr(value), _ptr(shp), _ptr(start), _ptr(loc), _ptr(aw),
-                                                      _ptr(out), ctypes.c_void_p(_stream_ptr(dev))))
-    return out
+    if torch.is_grad_enabled() and (value.requires_grad or loc.requires_grad or aw.requires_grad):
+        return _DeformAttn.apply(value, shp, start, loc, aw, out_dtype)
+    return _deform_fwd(value, shp, start, loc, aw, out_dtype)

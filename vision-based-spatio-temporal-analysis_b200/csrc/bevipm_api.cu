@@ -341,6 +341,29 @@ int launch_deform(const bevipm::DeformParams& p, int lph, cudaStream_t st) {
 }  // namespace
 
 
+namespace {
+template <typename TIn, typename TG>
+int launch_deform_bwd(const bevipm::DeformBwdParams& bp, int lph, cudaStream_t st) {
+    const bevipm::DeformParams& p = bp.f;
+    const long long npairs = (long long)p.B * p.Q * p.M;
+    const int pairs_per_warp = 32 / lph;
+    const long long warps = (npairs + pairs_per_warp - 1) / pairs_per_warp;
+    const long long blocks = (warps + 7) / 8;
+    if (blocks > 0x7fffffffLL) return fail(BEVIPM_ERR_UNSUPPORTED, "too many queries");
+#define BEVIPM_DEFORM_BWD_CASE(N) \
+    case N: bevipm::deform_attn_bwd_kernel<TIn, TG, N><<<(unsigned)blocks, 256, 0, st>>>(bp); break;
+    switch (lph) {
+        BEVIPM_DEFORM_BWD_CASE(1) BEVIPM_DEFORM_BWD_CASE(2) BEVIPM_DEFORM_BWD_CASE(4) BEVIPM_DEFORM_BWD_CASE(8)
+        BEVIPM_DEFORM_BWD_CASE(16) BEVIPM_DEFORM_BWD_CASE(32)
+        default: return fail(BEVIPM_ERR_UNSUPPORTED, "D*elem/16 = %d lanes per head is not a power of two <= 32", lph);
+    }
+#undef BEVIPM_DEFORM_BWD_CASE
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+}  // namespace
+
 namespace bevipm {
 // for the launchers that live in other translation units (bevipm_shard.cu)
 void note_launch(int variant) {
@@ -558,6 +581,34 @@ int bevipm_deform_attn_fwd(const bevipm_deform_desc* d, const void* value, const
     if (!v32 && !o32) return launch_deform<__nv_bfloat16, __nv_bfloat16>(p, lph, st);
     if (!v32 && o32) return launch_deform<__nv_bfloat16, float>(p, lph, st);
     return fail(BEVIPM_ERR_UNSUPPORTED, "fp32 value with bf16 output is not built");
+}
+
+int bevipm_deform_attn_bwd(const bevipm_deform_desc* d, const void* value, const int32_t* shapes, const int64_t* level_start,
+                           const float* loc, const float* attn, const void* grad_out, float* grad_value, float* grad_loc, float* grad_attn,
+                           void* stream) {
+    if (!d) return fail(BEVIPM_ERR_BAD_ARG, "desc is null");
+    if (d->B <= 0 || d->Q <= 0 || d->M <= 0 || d->D <= 0 || d->L <= 0 || d->P <= 0 || d->S <= 0)
+        return fail(BEVIPM_ERR_BAD_ARG, "non-positive extent");
+    if (!value || !shapes || !level_start || !loc || !attn || !grad_out || !grad_value || !grad_loc || !grad_attn)
+        return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if ((d->value_dtype != BEVIPM_F32 && d->value_dtype != BEVIPM_BF16) || (d->out_dtype != BEVIPM_F32 && d->out_dtype != BEVIPM_BF16))
+        return fail(BEVIPM_ERR_BAD_ARG, "unknown dtype");
+    const int esz = d->value_dtype == BEVIPM_F32 ? 4 : 2;
+    if ((d->D * esz) % 16 || d->D * esz > 512) return fail(BEVIPM_ERR_UNSUPPORTED, "D=%d: D*elem must be a multiple of 16 bytes, <= 512", d->D);
+    if (!aligned16(value) || !aligned16(grad_value) || (reinterpret_cast<uintptr_t>(loc) & 7) || (reinterpret_cast<uintptr_t>(grad_loc) & 7))
+        return fail(BEVIPM_ERR_BAD_ARG, "value / grad_value must be 16-byte aligned, loc / grad_loc 8-byte aligned");
+    bevipm::DeformBwdParams bp;
+    bevipm::DeformParams& p = bp.f;
+    p.value = value; p.shapes = shapes; p.start = reinterpret_cast<const long long*>(level_start); p.loc = loc; p.attn = attn; p.out = nullptr;
+    p.B = d->B; p.Q = d->Q; p.M = d->M; p.D = d->D; p.L = d->L; p.P = d->P; p.S = d->S;
+    bp.gout = grad_out; bp.gvalue = grad_value; bp.gloc = grad_loc; bp.gattn = grad_attn;
+    const int lph = d->D * esz / 16;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool v32 = d->value_dtype == BEVIPM_F32, g32 = d->out_dtype == BEVIPM_F32;
+    if (v32 && g32) return launch_deform_bwd<float, float>(bp, lph, st);
+    if (!v32 && g32) return launch_deform_bwd<__nv_bfloat16, float>(bp, lph, st);
+    if (!v32 && !g32) return launch_deform_bwd<__nv_bfloat16, __nv_bfloat16>(bp, lph, st);
+    return launch_deform_bwd<float, __nv_bfloat16>(bp, lph, st);
 }
 
 // ---- host-buffer entry: H2D -> kernel -> D2H, frame by frame, double buffered -----------------------

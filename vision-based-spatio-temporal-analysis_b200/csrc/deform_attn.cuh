@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "ipm_aux.cuh"
 #include "ipm_fused.cuh"
 
 namespace bevipm {
@@ -123,6 +124,109 @@ __global__ void __launch_bounds__(256) deform_attn_kernel(const DeformParams p) 
     if (live) {
         TOut* op = reinterpret_cast<TOut*>(p.out) + pair * p.D + sub * VE;
         store_pairs<TOut, PR>(op, acc);
+    }
+}
+
+}  // namespace bevipm
+
+namespace bevipm {
+
+// ---- backward ---------------------------------------------------------------------------------------------------------
+// d out / d value (scatter, fp32 atomics), d out / d sampling_locations and d out / d attention_weights (Deformable-DETR's
+// ms_deform_attn backward, restated from its published formulas).  Same mapping as the forward: LPH lanes own one (query,
+// head) pair, a lane owns 16 bytes of the head's channels.  Per sample the four taps are re-read, the lane forms its part of
+//     t   = sum_d g_d * (w00 v00 + w01 v01 + w10 v10 + w11 v11)_d          -> grad_attn = t (with the attention weight left out)
+//     gx  = sum_d g_d * (hy (v01 - v00) + ly (v11 - v10))_d * W * A         -> grad_loc.x
+//     gy  = sum_d g_d * (hx (v10 - v00) + lx (v11 - v01))_d * H * A         -> grad_loc.y
+// (taps outside the map count as zero), the LPH lanes add their parts by shuffle, lane 0 of the group stores the three
+// numbers, and every lane adds  g_d * w_tap * A  into grad_value at its four taps (red.global.add.v4.f32).
+struct DeformBwdParams {
+    DeformParams f;            // forward tensors (out unused)
+    const void* gout;          // [B,Q,M*D] TG
+    float* gvalue;             // [B,S,M,D] f32, pre-zeroed
+    float* gloc;               // [B,Q,M,L,P,2] f32
+    float* gattn;              // [B,Q,M,L,P] f32
+};
+
+template <typename TIn, typename TG, int LPH>
+__global__ void __launch_bounds__(256) deform_attn_bwd_kernel(const DeformBwdParams bp) {
+    using VT = VecTraits<TIn>;
+    constexpr int VE = VT::VE, PR = VT::P;
+    constexpr int PAIRS = 32 / LPH;
+    const DeformParams& p = bp.f;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long npairs = (long long)p.B * p.Q * p.M;
+    long long pair = warp * PAIRS + lane / LPH;
+    const bool live = pair < npairs;
+    if (!live) pair = 0;
+    const int sub = lane % LPH;
+    const int m = (int)(pair % p.M);
+    const int b = (int)(pair / p.M / p.Q);
+    const int LP = p.L * p.P;
+    const float2* loc = reinterpret_cast<const float2*>(p.loc) + pair * LP;
+    const float* aw = p.attn + pair * LP;
+    const long long head0 = ((long long)b * p.S * p.M + m) * p.D + sub * VE;   // element offset of this lane's channels at position 0
+    const TIn* vb = reinterpret_cast<const TIn*>(p.value) + head0;
+    float* gvb = bp.gvalue + head0;
+    const long long pos_stride = (long long)p.M * p.D;                          // elements per spatial position
+
+    // this lane's slice of dL/dout
+    float g[VE];
+    {
+        const TG* gp = reinterpret_cast<const TG*>(bp.gout) + pair * p.D + sub * VE;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) g[e] = live ? load_f32(gp + e) : 0.0f;
+    }
+    for (int s = 0; s < LP; ++s) {
+        const int l = s / p.P;
+        const int H = __ldg(p.shapes + 2 * l), W = __ldg(p.shapes + 2 * l + 1);
+        const long long st = __ldg(p.start + l);
+        const float2 xy = __ldg(loc + s);
+        const float a = __ldg(aw + s);
+        const float x = __fmaf_rn(xy.x, (float)W, -0.5f);
+        const float y = __fmaf_rn(xy.y, (float)H, -0.5f);
+        const bool inside = y > -1.0f && x > -1.0f && y < (float)H && x < (float)W;
+        float t = 0.0f, gx = 0.0f, gy = 0.0f;
+        if (inside) {   // (uniform within the head group: all its lanes share the sample)
+            const float x0f = floorf(x), y0f = floorf(y);
+            const float lx = x - x0f, ly = y - y0f, hx = 1.0f - lx, hy = 1.0f - ly;
+            const int x0 = (int)x0f, y0 = (int)y0f;
+            const bool xw = x0 >= 0, xe = x0 + 1 <= W - 1, yn = y0 >= 0, ysb = y0 + 1 <= H - 1;
+            const bool ok[4] = {yn && xw, yn && xe, ysb && xw, ysb && xe};
+            const float wt[4] = {hy * hx, hy * lx, ly * hx, ly * lx};
+            float v[4][VE];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const long long pos = (st + (long long)(y0 + (k >> 1)) * W + (x0 + (k & 1))) * pos_stride;
+#pragma unroll
+                for (int e = 0; e < VE; ++e) v[k][e] = ok[k] ? load_f32(vb + pos + e) : 0.0f;
+                if (ok[k] && live) {
+#pragma unroll
+                    for (int e = 0; e < VE; e += 4) {
+                        const float c = wt[k] * a;
+                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gvb + pos + e), "f"(g[e] * c), "f"(g[e + 1] * c),
+                                     "f"(g[e + 2] * c), "f"(g[e + 3] * c) : "memory");
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < VE; ++e) {
+                t += g[e] * (wt[0] * v[0][e] + wt[1] * v[1][e] + wt[2] * v[2][e] + wt[3] * v[3][e]);
+                gx += g[e] * (hy * (v[1][e] - v[0][e]) + ly * (v[3][e] - v[2][e]));
+                gy += g[e] * (hx * (v[2][e] - v[0][e]) + lx * (v[3][e] - v[1][e]));
+            }
+        }
+#pragma unroll
+        for (int o = LPH / 2; o > 0; o >>= 1) {
+            t += __shfl_xor_sync(0xffffffffu, t, o, LPH);
+            gx += __shfl_xor_sync(0xffffffffu, gx, o, LPH);
+            gy += __shfl_xor_sync(0xffffffffu, gy, o, LPH);
+        }
+        if (live && sub == 0) {
+            bp.gattn[pair * LP + s] = t;
+            reinterpret_cast<float2*>(bp.gloc)[pair * LP + s] = make_float2(gx * (float)W * a, gy * (float)H * a);
+        }
     }
 }
 
