@@ -187,10 +187,10 @@ def test_staged_full_size_fp32_vs_oracle(name, variant):
     assert _same(out, want)
 
 
-@pytest.mark.parametrize("variant", STAGED)
+@pytest.mark.parametrize("variant", [0] + STAGED)
 def test_staged_full_size_c2_all_frames_vs_oracle(variant):
     """BASELINE config 1 (the bench workload), every one of the 8 frames against the oracle, bit-exact, plus the
-    bf16 output = rounding of the fp32 output."""
+    bf16 output = rounding of the fp32 output.  variant 0 = the default dispatch (run kernel)."""
     from bevipm import _lib, ops, rig
     wl = rig.WORKLOADS["c2"]
     B, V, C = wl.frames, wl.views, wl.channels
@@ -208,4 +208,33 @@ def test_staged_full_size_c2_all_frames_vs_oracle(variant):
     for b in range(B):
         fb = f[b:b + 1].float().cpu().numpy()
         want = orc.warp_fuse(fb, K[None].numpy(), Rt[None].numpy(), xs.numpy(), ys.numpy(), img, "mean")
+        assert _same(out[b:b + 1].cpu().numpy(), want), b
+
+
+def test_full_size_c5_clip_every_frame_vs_oracle():
+    """BASELINE config 4 (c5): a 64-frame clip of c1's shape (7 views x 512 ch fp32) in ONE launch of the default kernel,
+    every frame against the oracle, bit-exact.  Frames 20..29 use another rig and frame 40 a one-bit-different extrinsic:
+    the frame groups must rebuild their tables exactly there."""
+    from bevipm import _lib, ops, rig
+    wl = rig.WORKLOADS["c5"]
+    B, V, C = wl.frames, wl.views, wl.channels
+    g = torch.Generator(device=DEV).manual_seed(7)
+    f = torch.empty((B, V, *wl.feat_hw, C), device=DEV)
+    for b in range(B):
+        f[b] = torch.randn((V, *wl.feat_hw, C), device=DEV, generator=g)
+    f = f.permute(0, 1, 4, 2, 3)
+    K0, R0 = rig.look_at_rig(V, 0)
+    K1, R1 = rig.look_at_rig(V, 1)
+    K = K0[None].repeat(B, 1, 1, 1)
+    Rt = R0[None].repeat(B, 1, 1, 1)
+    K[20:30], Rt[20:30] = K1, R1
+    Rt[40, 3, 1, 3] = torch.nextafter(Rt[40, 3, 1, 3], torch.tensor(float("inf")))
+    Kd, Rd = K.contiguous().to(DEV), Rt[:, :, :3, :].contiguous().to(DEV)
+    xs, ys = rig.ground_axes(*wl.bev_hw, wl.bounds)
+    out = ops.warp_fuse(f, Kd, Rd, xs.to(DEV), ys.to(DEV), wl.img_size[0], wl.img_size[1], _lib.MEAN, False, 0)
+    torch.cuda.synchronize()
+    assert out.shape == (B, C, *wl.bev_hw)
+    for b in range(B):
+        fb = f[b:b + 1].cpu().numpy()                      # channels-last strides travel with the array
+        want = orc.warp_fuse(fb, K[b:b + 1].numpy(), Rt[b:b + 1].numpy(), xs.numpy(), ys.numpy(), wl.img_size, "mean", channels_last_out=True)
         assert _same(out[b:b + 1].cpu().numpy(), want), b

@@ -199,15 +199,18 @@ __global__ void __launch_bounds__(256) deform_attn_bwd_kernel(const DeformBwdPar
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const long long pos = (st + (long long)(y0 + (k >> 1)) * W + (x0 + (k & 1))) * pos_stride;
+                float2 f[PR];
 #pragma unroll
-                for (int e = 0; e < VE; ++e) v[k][e] = ok[k] ? load_f32(vb + pos + e) : 0.0f;
+                for (int e = 0; e < PR; ++e) f[e] = make_float2(0.0f, 0.0f);
+                if (ok[k]) VT::unpack(ldg16(reinterpret_cast<const uint4*>(vb + pos)), f);   // one 16-byte load per tap and lane
+#pragma unroll
+                for (int e = 0; e < PR; ++e) { v[k][2 * e] = f[e].x; v[k][2 * e + 1] = f[e].y; }
                 if (ok[k] && live) {
+                    const float c = wt[k] * a;
 #pragma unroll
-                    for (int e = 0; e < VE; e += 4) {
-                        const float c = wt[k] * a;
+                    for (int e = 0; e < VE; e += 4)
                         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(gvb + pos + e), "f"(g[e] * c), "f"(g[e + 1] * c),
                                      "f"(g[e + 2] * c), "f"(g[e + 3] * c) : "memory");
-                    }
                 }
             }
 #pragma unroll
