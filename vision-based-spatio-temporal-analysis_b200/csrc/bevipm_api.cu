@@ -743,9 +743,32 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     const size_t texel_bytes = (size_t)d.C * ie, row_bytes = (size_t)d.Wf * texel_bytes, view_bytes = (size_t)d.Hf * row_bytes;
     int kBand = 16;  // source rows per 2-D copy (the union of their spans): 1 / 4 / 16 / 32 / whole view = 130 / 175 / 193 / 191 / 183 frames/s on config 1
     if (const char* e = getenv("BEVIPM_HOST_BAND")) kBand = std::max(1, atoi(e));
+    // Upload path: when the caller's features are pinned host memory the device can address (cudaHostAlloc / torch
+    // pin_memory under UVA), a gather kernel pulls exactly the sampled spans over PCIe (host_span_gather_kernel); pageable
+    // or unmapped memory takes the banded 2-D copies.  BEVIPM_HOST_GATHER=0 forces the copies (A/B aid).
+    const uint4* mapped = nullptr;
+    {
+        cudaPointerAttributes pa;
+        const char* g = getenv("BEVIPM_HOST_GATHER");
+        if (!(g && g[0] == '0') && cudaPointerGetAttributes(&pa, feats) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
+            texel_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(pa.devicePointer) & 15) == 0)
+            mapped = static_cast<const uint4*>(pa.devicePointer);
+        else
+            cudaGetLastError();  // (a pageable pointer makes cudaPointerGetAttributes report an error on old drivers: not ours)
+    }
     int64_t h2d = 0;
     for (int f = 0; f < B; ++f) {
         const int s = f & 1;
+        if (mapped) {
+            const int texel16 = (int)(texel_bytes / 16);
+            dim3 grid(2, (unsigned)(d.V * d.Hf));
+            bevipm::host_span_gather_kernel<<<grid, 256, 0, A.st[s]>>>(mapped + (size_t)f * (fbytes / 16), static_cast<uint4*>(A.feats[s]),
+                                                                       A.rows + 2 * (size_t)f * d.V * d.Hf, d.Wf, texel16);
+            g_launches.fetch_add(1, std::memory_order_relaxed);
+            CUDA_TRY(cudaGetLastError());
+            for (size_t q = (size_t)f * d.V * d.Hf; q < (size_t)(f + 1) * d.V * d.Hf; ++q)
+                if (A.rows_host[2 * q] <= A.rows_host[2 * q + 1]) h2d += (int64_t)(A.rows_host[2 * q + 1] - A.rows_host[2 * q] + 1) * (int64_t)texel_bytes;
+        } else
         for (int v = 0; v < d.V; ++v) {
             const int* sp = A.rows_host + 2 * ((size_t)f * d.V + v) * d.Hf;
             for (int y0 = 0; y0 < d.Hf; y0 += kBand) {
