@@ -511,14 +511,25 @@ def test_layout_prepass_and_view_reduction_kernels():
     assert torch.equal(ops.fuse_views(pv, "max"), pv.max(dim=1).values)
 
 
-def test_host_buffer_entry_matches_oracle():
+@pytest.mark.parametrize("pinned,gather", [(True, "1"), (True, "0"), (False, "1")])
+def test_host_buffer_entry_matches_oracle(monkeypatch, pinned, gather):
+    """Pinned features are pulled over PCIe by the span gather kernel; BEVIPM_HOST_GATHER=0 and pageable memory take the
+    banded 2-D copies.  Repeated calls with the same calibration re-use the cached span table; a new calibration rebuilds it."""
     from bevipm import ops
+    monkeypatch.setenv("BEVIPM_HOST_GATHER", gather)
     feats, K, Rt, xs, ys, img = _rig_case(3, 4, 32, (27, 48), (24, 72), seed=13)
-    host = torch.from_numpy(np.ascontiguousarray(feats.transpose(0, 1, 3, 4, 2))).pin_memory()
-    out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
-                             torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+    host = torch.from_numpy(np.ascontiguousarray(feats.transpose(0, 1, 3, 4, 2)))
+    if pinned:
+        host = host.pin_memory()
     want = orc.warp_fuse(feats, K, Rt, xs, ys, img, "mean")
-    assert _same(out.numpy().transpose(0, 3, 1, 2), want)
+    for _ in range(2):
+        out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                                 torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+        assert _same(out.numpy().transpose(0, 3, 1, 2), want)
+    feats2, K2, Rt2, _, _, _ = _rig_case(3, 4, 32, (27, 48), (24, 72), seed=14)
+    out = ops.warp_fuse_host(host, torch.from_numpy(K2), torch.from_numpy(Rt2[:, :, :3, :]).contiguous(),
+                             torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+    assert _same(out.numpy().transpose(0, 3, 1, 2), orc.warp_fuse(feats, K2, Rt2, xs, ys, img, "mean"))
 
 
 def test_host_buffer_entry_uploads_only_sampled_texels():

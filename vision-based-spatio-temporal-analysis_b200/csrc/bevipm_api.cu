@@ -223,7 +223,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     }
     if (variant == 0) {
         // Defaults, measured on every BASELINE shape (profiles/r01_notes.md):
-        //  * whole 512-byte channel chunks, sum/mean, V <= 16: the run kernel (taps re-used in registers along the
+        //  * channels-last features, V <= 32 (kRunMaxViews): the run kernel (taps re-used in registers along the
         //    row), one warp per row segment walking all chunks; fp32 at 96 registers (20 warps/SM), bf16 at 128
         //    (the unpacked block needs 32 registers).  c1 0.088 ms, c2 0.76-0.78 ms, c3 0.258 ms against the list
         //    kernel's 0.098 / 0.78-0.82 / 0.376.
@@ -422,7 +422,7 @@ int bevipm_warp_fuse_bwd(const bevipm_desc* d, const void* grad_out, const float
     const int64_t fs[] = {d->fs_b, d->fs_v, d->fs_y, d->fs_x};
     for (int64_t s : fs) if (s % 4) vec = false;
     // run-kernel backward (contributions of a row's cells summed per 2x2 block in registers before the atomics):
-    // channels-last fp32 gradient, whole 128-channel chunks, V <= 16; d->variant == 1 forces the generic kernel
+    // channels-last fp32 gradient, whole 128-channel chunks, V <= 32 (kRunMaxViews); d->variant == 1 forces the generic kernel
     const long long span16 = (long long)d->V * (d->fs_v / 4) + (long long)(d->Hf + 2) * (d->fs_y / 4) + (long long)(d->Wf + 2) * (d->fs_x / 4);
     const int og = g32 ? 4 : 4;  // grad_out is read 4 channels at a time: 16 bytes (fp32) or 8 bytes (bf16)
     const char* force_generic = getenv("BEVIPM_BWD_GENERIC");  // A/B aid (tools/bench_backward.py)
