@@ -747,9 +747,11 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     // pin_memory under UVA), a gather kernel pulls exactly the sampled spans over PCIe (host_span_gather_kernel); pageable
     // or unmapped memory takes the banded 2-D copies.  BEVIPM_HOST_GATHER=0 forces the copies (A/B aid).
     const uint4* mapped = nullptr;
+    int gather_mode = 1;   // 1: every frame through the gather kernel; 2: odd frames gather, even frames DMA (both PCIe read paths busy); 0: DMA only
     {
         cudaPointerAttributes pa;
         const char* g = getenv("BEVIPM_HOST_GATHER");
+        if (g && g[0] >= '0' && g[0] <= '2') gather_mode = g[0] - '0';
         if (!(g && g[0] == '0') && cudaPointerGetAttributes(&pa, feats) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer &&
             texel_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(pa.devicePointer) & 15) == 0)
             mapped = static_cast<const uint4*>(pa.devicePointer);
@@ -759,7 +761,7 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     int64_t h2d = 0;
     for (int f = 0; f < B; ++f) {
         const int s = f & 1;
-        if (mapped) {
+        if (mapped && (gather_mode == 1 || (f & 1))) {
             const int texel16 = (int)(texel_bytes / 16);
             dim3 grid(2, (unsigned)(d.V * d.Hf));
             bevipm::host_span_gather_kernel<<<grid, 256, 0, A.st[s]>>>(mapped + (size_t)f * (fbytes / 16), static_cast<uint4*>(A.feats[s]),
