@@ -532,6 +532,25 @@ def test_host_buffer_entry_matches_oracle(monkeypatch, pinned, gather):
     assert _same(out.numpy().transpose(0, 3, 1, 2), orc.warp_fuse(feats, K2, Rt2, xs, ys, img, "mean"))
 
 
+def test_host_buffer_entry_never_reads_unsampled_staging_memory(monkeypatch):
+    """The device staging arena is only partially written (sampled spans): with the arena poisoned with NaN patterns
+    (BEVIPM_HOST_POISON) the result must still be the oracle's -- no kernel reads a texel that was not uploaded."""
+    from bevipm import _lib, ops
+    _lib.load().bevipm_host_release()            # force a fresh (poisoned) arena
+    monkeypatch.setenv("BEVIPM_HOST_POISON", "1")
+    for dtype in (torch.float32, torch.bfloat16):
+        feats, K, Rt, xs, ys, img = _rig_case(2, 7, 256, (40, 64), (36, 100), seed=19)
+        f = torch.from_numpy(feats).to(dtype)
+        host = f.permute(0, 1, 3, 4, 2).contiguous().pin_memory()
+        for mode in ("mean", "max"):
+            out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                                     torch.from_numpy(xs), torch.from_numpy(ys), img, mode, out_dtype=torch.float32)
+            want = orc.warp_fuse(f.float().numpy(), K, Rt, xs, ys, img, mode)
+            assert _same(out.numpy().transpose(0, 3, 1, 2), want), (dtype, mode)
+        _lib.load().bevipm_host_release()
+    monkeypatch.delenv("BEVIPM_HOST_POISON")
+
+
 def test_host_buffer_entry_uploads_only_sampled_texels():
     """The host entry copies, per frame, view and band of source rows, only the span of texels some BEV cell samples.
     Every texel NO cell samples is poisoned with NaN in the HOST buffer: the result must still be the oracle's on the

@@ -625,6 +625,8 @@ struct HostArena {
     cudaStream_t st[2] = {nullptr, nullptr};
     cudaEvent_t calib_ready = nullptr;
     int device = -1;
+    // (no destructor on purpose: at process exit the CUDA runtime may be gone before thread-local destructors run;
+    //  a thread that is done with the entry calls bevipm_host_release(), see include/bevipm.h)
     void release() {
         for (int s = 0; s < 2; ++s) {
             if (feats[s]) cudaFree(feats[s]);
@@ -682,6 +684,9 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
         for (int s = 0; s < 2; ++s) {
             CUDA_TRY(cudaMalloc(&A.feats[s], fbytes));
             CUDA_TRY(cudaMalloc(&A.out[s], obytes));
+            // Only sampled spans are ever uploaded, so most of the staging buffer is never written: the kernels must not read
+            // it.  BEVIPM_HOST_POISON=1 (tests) fills it with NaN bit patterns so that a single stray read shows in the result.
+            if (getenv("BEVIPM_HOST_POISON")) CUDA_TRY(cudaMemset(A.feats[s], 0xFF, fbytes));
             CUDA_TRY(cudaStreamCreateWithFlags(&A.st[s], cudaStreamNonBlocking));
         }
         CUDA_TRY(cudaMalloc(&A.calib, cal_floats * 4));
