@@ -179,6 +179,26 @@ int bevipm_deform_attn_bwd(const bevipm_deform_desc *d, const void *value, const
                            float *grad_value, float *grad_loc, float *grad_attn, void *stream);
 
 /*
+ * BEVNet's 1x1 projection folded in front of the warp.  The reference concatenates the V warped maps
+ * and applies nn.Conv2d(V*C, Co, 1) on the BEV grid (model_wrapper.py:68-73); the warp is linear per channel, so
+ *   proj(concat_v(warp_v(f_v))) = sum_v warp_v(W_v f_v) + bias,   W_v = proj.weight[:, v*C:(v+1)*C],
+ * and the projection can run on the small source maps: out[m, r, :] = W_(m % V) . x[m, r, :] for every map m = b*V + v and
+ * source texel r.  A hand-written tcgen05 GEMM (csrc/bevipm_proj.cu: TMA-fed ring, kind::tf32 MMAs into a TMEM accumulator,
+ * TMA-store epilogue), device pointers, fp32:
+ *   x    [BV, rows, C]   element strides x_map_stride, x_row_stride, 1   (rows = Hf*Wf of channels-last maps)
+ *   w_hi [Co, V, C]      contiguous;  passes = 1: the weights themselves;  passes = 3: their TF32 heads (low 13 mantissa
+ *   w_lo [Co, V, C]      bits cleared) and w_lo = w - w_hi, the exact remainders (may be null when passes = 1)
+ *   out  [BV, rows, Co]  element strides out_map_stride, out_row_stride, 1
+ * passes = 1: one TF32 pass (the arithmetic cuDNN uses for the reference's Conv2d under torch's default allow_tf32);
+ * passes = 3: split operands, hi*hi + lo*hi + hi*lo, fp32-grade (~1e-6 relative).  Co: a multiple of 16 in [16, 256];
+ * C and all strides multiples of 4; 16-byte aligned pointers.  The same entry computes the input gradient of the
+ * projection (x := grad_out, w := the transposed weights).
+ */
+int bevipm_proj1x1(const float *x, const float *w_hi, const float *w_lo, float *out, int32_t BV, int32_t V, int64_t rows,
+                   int32_t C, int32_t Co, int64_t x_row_stride, int64_t x_map_stride, int64_t out_row_stride,
+                   int64_t out_map_stride, int32_t passes, void *stream);
+
+/*
  * Host-buffer entry (the call a non-torch integrator makes, and what bench.py's e2e times):
  * feats/out are HOST pointers (pinned for full PCIe rate) laid out as feats [B,V,Hf,Wf,C] and
  * out [B,Hb,Wb,C] ([B,V,Hb,Wb,C] for NONE); K, Rt34, xs, ys are host arrays.  Frames are streamed

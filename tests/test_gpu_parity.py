@@ -230,11 +230,31 @@ def test_run_kernel_non_finite_features_take_the_exact_division():
     assert np.isinf(want).any()
     for variant in (31, 33):
         out = _run(feats, K, Rt, xs, ys, img, "mean", True, variant=variant).cpu().numpy()
-        # cells whose block holds a non-finite texel next to an out-of-map tap may differ (documented: NaN for +-Inf)
-        both = np.isfinite(want) & np.isfinite(out)
-        assert np.array_equal(out[both], want[both])
-        assert np.array_equal(np.isinf(want) & ~np.isnan(out), np.isinf(out))
-        assert np.array_equal(out[np.isinf(out)], want[np.isinf(out)])
+        assert _same(out, want)
+
+
+@pytest.mark.parametrize("variant", [0, 31, 32, 33, 37])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_run_kernel_non_finite_features_on_the_map_border_match_the_reference_exactly(variant, dtype):
+    """Blocks that hang over the map's border: the reference pads with zeros (geometry.py:161), so an out-of-map tap
+    contributes w * 0 = +0 even when its in-map neighbours hold +-Inf / NaN.  The run kernel copies a stand-in texel
+    for such taps and clears their registers after the unpack; the result must equal the oracle everywhere (round 1
+    returned NaN where the reference returns +-Inf)."""
+    feats, K, Rt, xs, ys, img = _rig_case(2, 3, 256, (20, 33), (19, 45), seed=31)
+    feats[0, 1, 5, 7, 11] = np.inf
+    feats[0, 2, 9, 3, 20] = -np.inf
+    feats[0, 0, 64, 10, 10] = np.nan
+    feats[:, :, 3, 0, :] = np.inf       # the whole top border row of channel 3
+    feats[:, :, 4, :, 0] = -np.inf      # the left border column of channel 4
+    feats[:, :, 5, -1, -1] = np.inf
+    feats[1, :, 6, -1, :] = -np.inf     # bottom row
+    feats[1, :, 7, :, -1] = np.nan      # right column
+    f = torch.from_numpy(feats).to(dtype).float().numpy()
+    for mode in ("mean", "sum", "max", "none"):
+        want = orc.warp_fuse(f, K, Rt, xs, ys, img, mode)
+        assert np.isinf(want).any()
+        out = _run(f, K, Rt, xs, ys, img, mode, True, dtype=dtype, variant=variant).cpu().numpy()
+        assert _same(out, want), mode
 
 
 @pytest.mark.parametrize("seed", range(12))

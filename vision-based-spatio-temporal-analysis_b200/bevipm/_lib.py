@@ -32,6 +32,7 @@ EXPORTS = (
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
     "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant", "bevipm_host_last_h2d_bytes",
     "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish", "bevipm_deform_attn_bwd",
+    "bevipm_proj1x1",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -75,6 +76,10 @@ def load() -> ctypes.CDLL:
     L.bevipm_deform_attn_fwd.restype = ctypes.c_int
     L.bevipm_deform_attn_bwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, fp, fp, fp, vp]
     L.bevipm_deform_attn_bwd.restype = ctypes.c_int
+    i32, i64 = ctypes.c_int32, ctypes.c_int64
+    if hasattr(L, "bevipm_proj1x1"):   # (absent only from an older build loaded through BEVIPM_LIB for an A/B)
+        L.bevipm_proj1x1.argtypes = [fp, fp, fp, fp, i32, i32, i64, i32, i32, i64, i64, i64, i64, i32, vp]
+        L.bevipm_proj1x1.restype = ctypes.c_int
     for name in ("bevipm_warp_fuse_fwd", "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc",
                  "bevipm_fuse_views", "bevipm_warp_fuse_host", "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish"):
         getattr(L, name).restype = ctypes.c_int
@@ -104,6 +109,8 @@ def variant_name(v: int) -> str:
         return f"warp_fuse_run_kernel (variant {v})"
     if v == 55:
         return "warp_fuse_boxrun_kernel (run kernel, ring filled by TMA 2x2 box copies, variant 55)"
+    if v == 70:
+        return "proj1x1_tf32_kernel (tcgen05 TF32 GEMM of the folded 1x1 projection, variant 70)"
     if v == 60:
         return "warp_fuse_run_kernel<KM_RED> (partial sums added into peer slabs)"
     if 50 <= v <= 53:

@@ -308,21 +308,39 @@ class FoldedConcatProjIPM(_IPMBase):
     projection folded in FRONT of the warp.
 
     The warp is linear per channel, so  proj(concat_v(warp_v(f_v))) = sum_v warp_v(W_v f_v) + bias  with
-    W_v = proj.weight[:, v*C:(v+1)*C]: the per-view 1x1 convolution runs on the small source maps (one batched
-    GEMM, a library call), the fused SUM kernel then gathers `out_channels` instead of V*C channels per cell and
-    the [B,V*C,Hb,Wb] tensor never exists (7 x 1280 x 120 x 360 fp32 = 1.55 GB per frame at wildtrack.yaml).
-    A reassociation of the reference's arithmetic: equal within fp32 rounding (tests: 1e-4 relative), not bit-exact.
+    W_v = proj.weight[:, v*C:(v+1)*C]: the per-view 1x1 convolution runs on the small source maps (one launch of the
+    hand-written tcgen05 GEMM, csrc/bevipm_proj.cu), the fused SUM kernel then gathers `out_channels` instead of V*C
+    channels per cell and the [B,V*C,Hb,Wb] tensor never exists (7 x 1280 x 120 x 360 fp32 = 1.55 GB per frame at
+    wildtrack.yaml).  A reassociation of the reference's arithmetic: equal within fp32 rounding (tests: 1e-4 relative), not
+    bit-exact.
+
+    precision: "fp32" (default) = split-operand TF32 (three MMAs per step, ~1e-6 relative: comparable with the fp32 Conv2d the
+    reference runs on the CPU), "tf32" = one TF32 pass (what cuDNN runs for the reference's Conv2d on a GPU under torch's
+    default `torch.backends.cudnn.allow_tf32 = True`, ~1e-3), "auto" = "tf32" iff that torch switch is on.
+    gemm: "auto" (default) = our tcgen05 kernel whenever it takes the shape (out_channels a multiple of 16 up to 256, C a
+    multiple of 4), torch.einsum (cuBLAS) otherwise; "tcgen05" = our kernel or an error; "cublas" = the round-1 path, kept for
+    comparison.  `last_gemm` names the one the last forward used.
 
     `proj` is the nn.Conv2d(V*C, out_channels, 1) the reference builds lazily (model_wrapper.py:70-72); it stays
     the owner of weight and bias, so checkpoints load unchanged and gradients reach it through the GEMM.
     """
 
-    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, proj: nn.Conv2d, views: int, variant: int = 0):
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, proj: nn.Conv2d, views: int, variant: int = 0,
+                 precision: str = "fp32", gemm: str = "auto"):
         super().__init__(bev_h, bev_w, bev_bounds)
         assert proj.kernel_size == (1, 1) and proj.in_channels % views == 0
+        assert precision in ("fp32", "tf32", "auto") and gemm in ("auto", "tcgen05", "cublas")
         self.proj = proj
         self.views = views
         self.variant = variant
+        self.precision = precision
+        self.gemm = gemm
+        self.last_gemm = None
+
+    def _passes(self) -> int:
+        if self.precision == "auto":
+            return 1 if torch.backends.cudnn.allow_tf32 else 3
+        return 1 if self.precision == "tf32" else 3
 
     def forward(self, feats: torch.Tensor, intrinsics, extrinsics,
                 img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
@@ -331,7 +349,13 @@ class FoldedConcatProjIPM(_IPMBase):
         Co = self.proj.out_channels
         W = self.proj.weight.view(Co, V, C).to(torch.float32)                      # [Co,V,C]
         x = feats.to(torch.float32).permute(0, 1, 3, 4, 2)                        # [B,V,Hf,Wf,C] (view, no copy if channels-last)
-        g = torch.einsum("bvhwc,ovc->bvhwo", x, W)                                 # per-view 1x1 conv, channels-last result
+        use_ours = self.gemm == "tcgen05" or (self.gemm == "auto" and ops.proj1x1_supported(C, Co))
+        self.last_gemm = "tcgen05" if use_ours else "cublas"
+        if not use_ours:
+            g = torch.einsum("bvhwc,ovc->bvhwo", x, W)                             # per-view 1x1 conv, channels-last result
+        else:
+            x = x.contiguous()                                                     # NCHW input: one transposing copy
+            g = ops.proj1x1(x.view(B * V, Hf * Wf, C), W, self._passes()).view(B, V, Hf, Wf, Co)
         g = g.permute(0, 1, 4, 2, 3)                                               # logical [B,V,Co,Hf,Wf], NHWC in memory
         out = self._run(g, intrinsics, extrinsics, img_size, _lib.SUM, False, self.variant, "keep")
         if self.proj.bias is not None:

@@ -400,3 +400,86 @@ def deform_attn(value: torch.Tensor, spatial_shapes: torch.Tensor, level_start_i
     if torch.is_grad_enabled() and (value.requires_grad or loc.requires_grad or aw.requires_grad):
         return _DeformAttn.apply(value, shp, start, loc, aw, out_dtype)
     return _deform_fwd(value, shp, start, loc, aw, out_dtype)
+
+
+# ---- BEVNet's 1x1 projection on the source maps: hand-written tcgen05 GEMM (csrc/bevipm_proj.cu) ----------------------
+
+def split_tf32(w: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """w = hi + lo with hi = w's TF32 head (the low 13 mantissa bits cleared) and lo the exact fp32 remainder."""
+    w = w.contiguous().float()
+    hi = (w.view(torch.int32) & -8192).view(torch.float32)
+    return hi, (w - hi).contiguous()
+
+
+def proj1x1_supported(C: int, Co: int) -> bool:
+    return C % 4 == 0 and Co % 16 == 0 and 16 <= Co <= 256
+
+
+def _proj1x1_raw(x: torch.Tensor, w: torch.Tensor, out: torch.Tensor, passes: int) -> torch.Tensor:
+    """x [BV,rows,C] fp32 (unit channel stride), w [Co,V,C] fp32, out [BV,rows,Co] fp32 (unit channel stride; may be a
+    channel slice of a wider tensor): out[m,r,:] = w[:, m % V, :] @ x[m,r,:]."""
+    BV, rows, C = x.shape
+    Co, V, C2 = w.shape
+    assert C2 == C and out.shape == (BV, rows, Co) and x.stride(2) == 1 and out.stride(2) == 1 and BV % V == 0
+    if passes == 3:
+        w_hi, w_lo = split_tf32(w)
+    else:
+        w_hi, w_lo = w.contiguous().float(), None
+    dev = x.device
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().bevipm_proj1x1(_ptr(x), _ptr(w_hi), _ptr(w_lo) if w_lo is not None else None, _ptr(out), BV, V, rows, C, Co,
+                                              x.stride(1), x.stride(0), out.stride(1), out.stride(0), passes,
+                                              ctypes.c_void_p(_stream_ptr(dev))))
+    return out
+
+
+class _Proj1x1(torch.autograd.Function):
+    """Forward and input gradient on the tcgen05 kernel; the weight gradient (a reduction over all texels, both operands
+    MN-major) is one torch.einsum."""
+
+    @staticmethod
+    def forward(ctx, x, w, passes):
+        ctx.save_for_backward(x, w)
+        ctx.passes = passes
+        BV, rows, _ = x.shape
+        out = torch.empty((BV, rows, w.shape[0]), device=x.device, dtype=torch.float32)
+        return _proj1x1_raw(x, w, out, passes)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        Co, V, C = w.shape
+        BV, rows, _ = x.shape
+        g = g.contiguous()
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.empty_like(x, memory_format=torch.contiguous_format)
+            wt = w.permute(2, 1, 0).contiguous()                          # [C, V, Co]: the transposed weights of every view
+            if proj1x1_supported(Co, 16):
+                for n0 in range(0, C, 256):                               # N of one launch is at most 256
+                    n1 = min(C, n0 + 256)
+                    if (n1 - n0) % 16:
+                        gx[:, :, n0:n1] = torch.einsum("mvro,ovc->mvrc", g.view(BV // V, V, rows, Co), w[:, :, n0:n1]).reshape(BV, rows, n1 - n0)
+                    else:
+                        _proj1x1_raw(g, wt[n0:n1], gx[:, :, n0:n1], ctx.passes)
+            else:
+                gx = torch.einsum("mvro,ovc->mvrc", g.view(BV // V, V, rows, Co), w).reshape(BV, rows, C)
+        if ctx.needs_input_grad[1]:
+            gw = torch.einsum("mvro,mvrc->ovc", g.view(BV // V, V, rows, Co), x.reshape(BV // V, V, rows, C))
+        return gx, gw, None
+
+
+def proj1x1(x: torch.Tensor, w: torch.Tensor, passes: int = 3) -> torch.Tensor:
+    """Per-view 1x1 projection on channels-last source maps: x [BV,rows,C] fp32, w [Co,V,C] -> [BV,rows,Co] fp32.
+    passes = 1: one TF32 pass; 3: split operands (fp32-grade).  model_wrapper.py:70-73 folded in front of the warp."""
+    if not x.is_cuda:
+        raise RuntimeError("bevipm runs on CUDA tensors only: there is no CPU implementation of this path")
+    if x.dtype != torch.float32 or x.dim() != 3 or w.dim() != 3 or x.stride(2) != 1:
+        raise ValueError("proj1x1 expects x [BV,rows,C] float32 with unit channel stride and w [Co,V,C]")
+    if not proj1x1_supported(x.shape[2], w.shape[0]):
+        raise ValueError(f"proj1x1: C={x.shape[2]} must be a multiple of 4 and Co={w.shape[0]} a multiple of 16 in [16, 256]")
+    w = w.to(device=x.device, dtype=torch.float32)
+    if torch.is_grad_enabled() and (x.requires_grad or w.requires_grad):
+        return _Proj1x1.apply(x, w, passes)
+    out = torch.empty((x.shape[0], x.shape[1], w.shape[0]), device=x.device, dtype=torch.float32)
+    return _proj1x1_raw(x, w, out, passes)

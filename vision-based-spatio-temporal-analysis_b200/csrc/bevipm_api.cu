@@ -11,7 +11,7 @@
 #include "ipm_aux.cuh"
 #include "ipm_fused.cuh"
 #include "ipm_list.cuh"
-#include "ipm_run.cuh"
+#include "run_launch.cuh"
 #include "ipm_run_bwd.cuh"
 #include "deform_attn.cuh"
 #include "staged_api.h"
@@ -136,44 +136,10 @@ int launch_list(FwdParams p, cudaStream_t st) {
     return 0;
 }
 
-// ---- run kernel (view-major walk, 2x2 blocks re-used in registers) ------------------------------------
-template <typename TIn>
-bool run_kernel_ok(const FwdParams& p) {
-    constexpr int VE = bevipm::VecTraits<TIn>::VE;
-    if (p.V > bevipm::kRunMaxViews) return false;
-    return (long long)p.V * (p.fs_v / VE) + (long long)(p.Hf + 2) * (p.fs_y / VE) + (long long)(p.Wf + 2) * (p.fs_x / VE) <= 0x7fffffffLL;
-}
-
-template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = bevipm::KM_ACC, bool TMA = false, bool HALF = false>
-int launch_run(FwdParams p, cudaStream_t st) {
-    constexpr int VE = bevipm::VecTraits<TIn>::VE;
-    constexpr int R = NW / KSPLIT;
-    if (TMA && p.C % (32 * VE)) return fail(BEVIPM_ERR_UNSUPPORTED, "the TMA ring copies whole 512-byte chunks: C must be a multiple of %d", 32 * VE);
-    if (!run_kernel_ok<TIn>(p) || (p.mode == BEVIPM_MAX) != (KMODE == bevipm::KM_MAX) || (p.mode == BEVIPM_NONE) != (KMODE == bevipm::KM_NONE))
-        return fail(BEVIPM_ERR_UNSUPPORTED, "run kernel: needs V <= %d, 32-bit tap offsets, and the variant of the fusion mode", bevipm::kRunMaxViews);
-    p.tiles_x = ceil_div(p.Wb, CELLS);
-    p.tiles_y = ceil_div(p.Hb, R);
-    p.fsy16 = (int)(p.fs_y / VE);
-    p.fsx16 = (int)(p.fs_x / VE);
-    p.rcpV = 1.0f / (float)p.V;
-    auto kern = bevipm::warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE, TMA, HALF>;
-    const size_t smem = (size_t)bevipm::run_tables_bytes(p.V, CELLS, R) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8;  // tables, rings, homographies, ring barriers
-    if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // frames per CTA: the phase A tables are shared by consecutive frames with the same calibration; keep
-    // at least ~16 CTA waves so the tail stays small
-    int fpc = 1;
-    {
-        const long long tiles = (long long)p.tiles_x * p.tiles_y;
-        const long long slots = 148LL * (65536 / (MAXREG * 32 * NW));
-        while (fpc < 8 && fpc * 2 <= p.B && tiles * ceil_div(p.B, fpc * 2) >= 16 * slots) fpc *= 2;
-        if (const char* e = getenv("BEVIPM_RUN_FPC")) fpc = std::max(1, std::min(atoi(e), p.B));
-    }
-    dim3 grid(p.tiles_x * p.tiles_y, 1, ceil_div(p.B, fpc));
-    kern<<<grid, NW * 32, smem, st>>>(p, fpc);
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
-}
+// ---- run kernel (view-major walk, 2x2 blocks re-used in registers): launcher in run_launch.cuh; the default
+// instantiations (variants 32 / 33 and the max / per-view walks) are compiled in their own translation unit, bevipm_run.cu
+using bevipm::launch_run;
+using bevipm::run_kernel_ok;
 
 // ---- TMA-staged kernel (ipm_staged.cuh; launcher in bevipm_staged.cu) ---------------------------------------------
 template <typename TIn, typename TOut>
@@ -203,7 +169,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         if (variant == 1 || span > 0x7fffffffLL) { g_last_variant = 1; return launch_fused<TIn, TOut, 1, 2, bevipm::KM_MAX, 3, false>(p, st); }
         if (variant != 21 && run_kernel_ok<TIn>(p)) {  // the run kernel's max walk
             g_last_variant = 33;
-            return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, bevipm::KM_MAX>(p, st);
+            return bevipm::launch_run_default(p, sizeof(TIn) == 2, sizeof(TOut) == 2, bevipm::KM_MAX, 128, st);
         }
         const long long texel_bytes = (long long)p.C * (long long)sizeof(TIn);
         if (texel_bytes >= 2048) { g_last_variant = 21; return launch_list<TIn, TOut, 4, bevipm::KM_MAX, 4, 3>(p, st); }
@@ -216,7 +182,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         // the tile kernel otherwise or when the caller forces it (variant 1)
         if (variant != 1 && run_kernel_ok<TIn>(p)) {
             g_last_variant = 32;
-            return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_NONE>(p, st);
+            return bevipm::launch_run_default(p, sizeof(TIn) == 2, sizeof(TOut) == 2, bevipm::KM_NONE, 96, st);
         }
         g_last_variant = 1;
         return launch_fused<TIn, TOut, 1, 2, bevipm::KM_NONE, 3, false>(p, st);
@@ -239,6 +205,14 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
     }
     g_last_variant = variant;
     switch (variant) {
+#ifdef BEVIPM_QUICK  // development builds (A/B of one kernel change): only the default kernels are instantiated
+        case 7: return launch_fused<TIn, TOut, 4, 1, bevipm::KM_ACC, 2, false>(p, st);
+        case 21: return launch_list<TIn, TOut, 4, bevipm::KM_ACC, 4, 3>(p, st);
+        case 23: return launch_list<TIn, TOut, 2, bevipm::KM_ACC, 4, 4>(p, st);
+        case 27: return launch_list<TIn, TOut, 1, bevipm::KM_ACC, 4, 4>(p, st);
+        case 32: return bevipm::launch_run_default(p, sizeof(TIn) == 2, sizeof(TOut) == 2, bevipm::KM_ACC, 96, st);
+        case 33: return bevipm::launch_run_default(p, sizeof(TIn) == 2, sizeof(TOut) == 2, bevipm::KM_ACC, 128, st);
+#else
         case 1: return launch_fused<TIn, TOut, 1, 2, bevipm::KM_ACC, 4, false>(p, st);
         case 2: return launch_fused<TIn, TOut, 1, 8, bevipm::KM_ACC, 2, false>(p, st);
         case 3: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_ACC, 2, false>(p, st);
@@ -261,8 +235,8 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         // 32 = fp32 default, 33 = bf16 default; the others are the sweep points quoted in profiles/r01_notes.md
         case 30: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_ACC, false, true>(p, st);   // half reloads
         case 31: return launch_run<TIn, TOut, 8, 4, 4, 128, 4, false>(p, st);
-        case 32: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);
-        case 33: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
+        case 32: return bevipm::launch_run_default(p, sizeof(TIn) == 2, sizeof(TOut) == 2, bevipm::KM_ACC, 96, st);
+        case 33: return bevipm::launch_run_default(p, sizeof(TIn) == 2, sizeof(TOut) == 2, bevipm::KM_ACC, 128, st);
         case 34: return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, bevipm::KM_ACC, false, true>(p, st);  // half reloads
         case 35: return launch_run<TIn, TOut, 8, 4, 4, 168, 4, false>(p, st);
         case 36: return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, bevipm::KM_ACC, true>(p, st);    // TMA ring
@@ -275,6 +249,7 @@ int dispatch_fused(const FwdParams& p, int variant, cudaStream_t st) {
         case 12: return launch_fused<TIn, TOut, 2, 2, bevipm::KM_PROBE, 2, false>(p, st);
         case 13: return launch_fused<TIn, TOut, 2, 4, bevipm::KM_PROBE, 2, false>(p, st);
         case 14: return launch_fused<TIn, TOut, 4, 2, bevipm::KM_PROBE, 2, false>(p, st);
+#endif
         default: break;
     }
     return fail(BEVIPM_ERR_UNSUPPORTED, "variant %d is not built", variant);
@@ -365,7 +340,8 @@ int launch_deform_bwd(const bevipm::DeformBwdParams& bp, int lph, cudaStream_t s
 }  // namespace
 
 namespace bevipm {
-// for the launchers that live in other translation units (bevipm_shard.cu)
+// for the launchers that live in other translation units (bevipm_shard.cu, bevipm_run.cu, bevipm_proj.cu)
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 void note_launch(int variant) {
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g_last_variant = variant;

@@ -22,12 +22,16 @@
 //            entry DEPTH-1 ahead to the copy engine; then blend `cur` with the cell's weights and add
 //            to the cell's accumulator (predicated on "seen").  Per cell the views are still added in
 //            ascending order: the reference's accumulation order.
-//   A tap outside the map gets weight 0 and the address of one of the block's in-map taps (exactly +0
-//   for finite features, as in the list kernel).
+//   A tap outside the map gets weight 0 and the address of one of the block's in-map taps; the walk zeroes the
+//   registers of such taps after the unpack (views that have a border block in the segment carry a flag and
+//   per-tap cell masks, everybody else pays one uniform test per view), so the tap contributes w * 0 = +0
+//   whatever the stand-in texel holds: the reference's zero padding, also next to +-Inf / NaN features.
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include <type_traits>
 
 #include "ipm_fused.cuh"
 
@@ -42,7 +46,7 @@ __host__ __device__ constexpr int run_tables_bytes(int V, int cells, int R);
 __host__ __device__ constexpr int run_seg_bytes(int V, int cells) {
     return V * cells * 16                    // blend weights (nw, ne, sw, se) of every (view, cell)
            + (V * cells + 8) * 16            // the load list (+8: entries the walk reads ahead but never copies)
-           + ((V * 12 + 12 + 15) / 16) * 16;  // per-view masks, view list, totals, cells every view sees, half-reload masks
+           + ((V * 20 + 12 + 15) / 16) * 16;  // per-view masks, view list, totals, cells every view sees, half-reload masks, border-tap masks
 }
 
 __host__ __device__ constexpr int run_tables_bytes(int V, int cells, int R) { return (R * run_seg_bytes(V, cells) + 127) / 128 * 128; }
@@ -60,6 +64,9 @@ __device__ __forceinline__ uint4 lds16(uint32_t addr) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
     return v;
+}
+__device__ __forceinline__ void sts16z(uint32_t addr) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
 __device__ __forceinline__ int4 lds16i(uint32_t addr) {
     int4 v;
@@ -112,6 +119,9 @@ __device__ __forceinline__ void run_copy_entry(uint32_t stage, unsigned long lon
 // column in registers; per view, ml[2V+3+v] = half bits | (moved-to-the-east bits << 16).
 // BOX: the load list holds texel coordinates instead of tap offsets ({x0 | y0 << 16, view, -, -}; end of list: view -1),
 // for rings that are filled by one tensor-map [2 x 2] box copy per reload (ipm_boxrun.cuh).
+// Border blocks (forward walk over tap offsets only, i.e. neither MARK_INVALID nor BOX): bit 16 of a view's mask word -- the
+// reload bit of cell 0, which always equals its seen bit -- says instead "some reload of this view has an out-of-map tap", and
+// ml[3V+3+2v] / ml[3V+4+2v] hold, per tap (NW | NE << 16, SW | SE << 16), the cells whose reload must zero that tap.
 template <int CELLS, bool WANT_ALL_SEEN, bool MARK_INVALID, bool HALF = false, bool BOX = false>
 __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int i, int j0, int lane, int fsv16, const float* sH,
                                                  float4* wts, int4* loads, int* ml) {
@@ -153,7 +163,18 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
             east_b = __ballot_sync(0xffffffffu, east);
         }
         const int shift = gl * CELLS;
-        const unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
+        unsigned seen_c = (seen_b >> shift) & CMASK, reload_c = (reload_b >> shift) & CMASK;
+        unsigned bz0 = 0, bz1 = 0;
+        if constexpr (!MARK_INVALID && !BOX) {
+            const unsigned inv = (reload && !(t.flags & kNonFinite)) ? (~(unsigned)t.flags & (unsigned)kTapMask) : 0u;
+            if (__any_sync(0xffffffffu, inv != 0)) {  // warp-uniform, rare: only segments on the rim of a view's footprint
+                const unsigned i0 = (__ballot_sync(0xffffffffu, inv & 1u) >> shift) & CMASK, i1 = (__ballot_sync(0xffffffffu, inv & 2u) >> shift) & CMASK;
+                const unsigned i2 = (__ballot_sync(0xffffffffu, inv & 4u) >> shift) & CMASK, i3 = (__ballot_sync(0xffffffffu, inv & 8u) >> shift) & CMASK;
+                bz0 = i0 | (i1 << 16);
+                bz1 = i2 | (i3 << 16);
+            }
+            reload_c = (reload_c & ~1u) | ((bz0 | bz1) ? 1u : 0u);  // bit 16 of the mask word: the view has border blocks
+        }
         const bool lead_seen = active && c == 0 && seen_c != 0;
         const unsigned lead_b = __ballot_sync(0xffffffffu, lead_seen);
         if (active) {
@@ -182,6 +203,7 @@ __device__ __forceinline__ void run_build_tables(const FwdParams& p, int V, int 
             }
             if (c == 0) {
                 ml[v] = (int)(seen_c | (reload_c << 16));
+                if (!MARK_INVALID && !BOX) { ml[3 * V + 3 + 2 * v] = (int)bz0; ml[3 * V + 4 + 2 * v] = (int)bz1; }
                 if (HALF) ml[2 * V + 3 + v] = (int)(((half_b >> shift) & CMASK) | (((east_b >> shift) & CMASK) << 16));
             }
             if (lead_seen) ml[V + nseen + __popc(lead_b & lt)] = v;
@@ -402,7 +424,22 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                     float4 wn = lds16f(wv);
                     // A cell the view does not see is never a reload; its blend runs on whatever `cur` holds
                     // and is simply not added (predicated), so the only branch per cell is "reload?".
-                    bool rl = (m >> 16) & 1u;
+                    bool rl = m & 1u;                    // cell 0 starts a block iff the view sees it
+                    const bool bview = (m >> 16) & 1u;  // some block of this view hangs over the map's border (warp-uniform, rare)
+                    // the reference pads with zeros (geometry.py:161 padding_mode='zeros'): before a border block is read back from
+                    // the ring, every lane overwrites its 16 bytes of the out-of-map taps (stand-in texels) with zeros, so whatever
+                    // the stand-in holds never reaches the blend (w * 0 = +0).  A lane reads back only bytes it wrote itself.
+                    auto patch_border = [&](int c, uint32_t st) {
+                        const int z0 = lds4i(s_meta + 4 * (3 * V + 3 + 2 * v)), z1 = lds4i(s_meta + 4 * (3 * V + 4 + 2 * v));
+                        if ((z0 >> c) & 1) sts16z(st);
+                        if ((z0 >> (16 + c)) & 1) sts16z(st + 512);
+                        if ((z1 >> c) & 1) sts16z(st + 1024);
+                        if ((z1 >> (16 + c)) & 1) sts16z(st + 1536);
+                    };
+                    // two copies of the walk: views with border blocks (rare) patch the ring before every read-back, everybody else
+                    // runs the copy without the test
+                    auto walk_cells = [&](auto border_tag) {
+                    constexpr bool BORDER = decltype(border_tag)::value;
 #pragma unroll
                     for (int c = 0; c < CELLS; ++c) {
                         const float4 w = wn;
@@ -415,6 +452,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                                 const uint32_t stc = n_cons & (DEPTH - 1);
                                 mbar_wait(bars + stc * 8, (n_cons / DEPTH) & 1u);  // the entry's 2048 bytes have landed
                                 const uint32_t sr = ring + stc * 2048;
+                                if constexpr (BORDER) patch_border(c, sr);
                                 uint4 nxt[4];
                                 nxt[0] = lds16(sr); nxt[1] = lds16(sr + 512);
                                 nxt[2] = lds16(sr + 1024); nxt[3] = lds16(sr + 1536);
@@ -448,6 +486,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                             st_rd = (st_rd == ring + (DEPTH - 1) * 2048) ? ring : st_rd + 2048;
                             } else {
                             cp_async_wait<DEPTH - 2>();  // the oldest entry has landed (a lane reads back its own bytes)
+                            if constexpr (BORDER) patch_border(c, st_rd);
                             uint4 nxt[4];
                             nxt[0] = lds16(st_rd); nxt[1] = lds16(st_rd + 512);
                             nxt[2] = lds16(st_rd + 1024); nxt[3] = lds16(st_rd + 1536);
@@ -492,7 +531,7 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                                         for (int q = 0; q < P; ++q) z[q] = seen ? sv[q] : make_float2(0.0f, 0.0f);
                                         store_pairs<TOut, P>(ovb + (long long)v * p.os_v + (long long)c * p.os_x, z);
                                     }
-                                } else
+                                } else {
 #pragma unroll
                                 for (int q = 0; q < ILP; ++q)
                                     if (seen) {
@@ -504,9 +543,13 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
                                             acc[c][q0 + q] = __fadd2_rn(acc[c][q0 + q], sv[q]);  // fusion.py:18-21, views ascending per cell
                                         }
                                     }
+                                }
                             }
                         }
                     }
+                    };
+                    if (!bview) walk_cells(std::false_type{});   // (this order keeps the common copy first in the code)
+                    else walk_cells(std::true_type{});
                 }
                 if constexpr (!TMA) cp_async_wait<0>();  // (only empty groups are left) the ring restarts with the next item
             }
