@@ -173,3 +173,106 @@ def test_deform_attn_fusion_module_trains():
     for name, prm in mod.named_parameters():
         assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
     assert float(mod.sampling_offsets.weight.grad.abs().max()) > 0 and float(mod.attention_weights.weight.grad.abs().max()) > 0
+
+
+# ---- the fused, image-space form: queries sample the SOURCE maps around their IPM position (no per-view BEV maps) -------
+
+def _rig(B, V, dev="cuda"):
+    from bevipm import rig
+    K, Rt = rig.look_at_rig(V, 3)
+    return K[None].expand(B, -1, -1, -1).contiguous().to(dev), Rt[None].expand(B, -1, -1, -1).contiguous().to(dev)
+
+
+def _identity_(mod):
+    with torch.no_grad():
+        for lin in (mod.value_proj, mod.output_proj):
+            lin.weight.copy_(torch.eye(lin.weight.shape[0]))
+            lin.bias.zero_()
+        mod.sampling_offsets.weight.zero_()
+        mod.sampling_offsets.bias.zero_()
+        mod.attention_weights.weight.zero_()
+        mod.attention_weights.bias.zero_()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mask_invalid", [False, True])
+def test_image_space_fusion_with_identity_parameters_is_the_reference_mean(mask_invalid):
+    """Zero offsets, uniform weights, identity projections: the module must reproduce GeometryTransformer -> SimpleFusion('mean')
+    (geometry.py:142-162 + fusion.py:20-21), i.e. the oracle-pinned fused kernel, up to the rounding of the two bilinear forms
+    (1e-4 of the largest value); with mask_invalid the mean over the views that see the cell (fusion='mean_valid')."""
+    import bevipm
+    from bevipm import rig
+    torch.manual_seed(0)
+    B, V, C, fhw, bhw = 2, 5, 64, (27, 48), (24, 72)
+    K, Rt = _rig(B, V)
+    feats = torch.randn(B, V, C, *fhw, device="cuda")
+    mod = bevipm.ImageSpaceDeformAttnFusion(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS, C, V, heads=4, points=3, mask_invalid=mask_invalid).cuda()
+    _identity_(mod)
+    with torch.no_grad():
+        out = mod(feats, K, Rt, img_size=rig.WILDTRACK_IMG_SIZE)
+        want = bevipm.FusedIPM(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS, fusion="mean_valid" if mask_invalid else "mean").cuda()(
+            feats, K, Rt, img_size=rig.WILDTRACK_IMG_SIZE)
+    assert out.shape == want.shape == (B, C, *bhw)
+    Kp, Rp = bevipm.pack_calibration(K, Rt, B, V, "cuda")
+    _, seen = mod.reference_points(Kp, Rp, fhw, rig.WILDTRACK_IMG_SIZE)
+    assert 0.05 < float(seen.float().mean()) < 0.95          # the rig has views that miss cells: masking matters
+    assert float((out - want).abs().max()) <= 1e-4 * float(want.abs().max())
+
+
+@pytest.mark.gpu
+def test_image_space_fusion_matches_oracle_composition():
+    """Random parameters: the same projections on the CPU, the oracle's sample positions (pinned to the reference) as
+    reference points and the from-spec deformable-attention oracle doing the sampling."""
+    import bevipm
+    from bevipm import rig
+    from oracle import ipm_oracle as orc
+    torch.manual_seed(1)
+    B, V, C, fhw, bhw = 1, 3, 32, (20, 33), (12, 30)
+    M, P, D = 4, 2, 8
+    K, Rt = _rig(B, V, "cpu")
+    feats = torch.randn(B, V, C, *fhw)
+    mod = bevipm.ImageSpaceDeformAttnFusion(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS, C, V, heads=M, points=P)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.05)
+        mod.attention_weights.weight.normal_(0, 0.2)
+    out = mod.cuda()(feats.cuda(), K.cuda(), Rt.cuda(), img_size=rig.WILDTRACK_IMG_SIZE).detach().cpu()
+    mod = mod.cpu()
+    xs, ys = rig.ground_axes(bhw[0], bhw[1], rig.WILDTRACK_BOUNDS)
+    Kn, Rn = K.numpy(), Rt.numpy()
+    with torch.no_grad():
+        Q, Hf, Wf = bhw[0] * bhw[1], fhw[0], fhw[1]
+        bev = torch.from_numpy(orc.warp_fuse(feats.numpy(), Kn, Rn, xs.numpy(), ys.numpy(), rig.WILDTRACK_IMG_SIZE, "mean"))
+        query = bev.permute(0, 2, 3, 1).reshape(B, Q, C)
+        ix, iy = orc.coords(Kn, Rn, xs.numpy(), ys.numpy(), fhw, rig.WILDTRACK_IMG_SIZE)
+        ix, iy = torch.from_numpy(np.asarray(ix)).view(B, V, Q), torch.from_numpy(np.asarray(iy)).view(B, V, Q)
+        ok = torch.isfinite(ix) & torch.isfinite(iy)
+        ref = torch.stack([torch.where(ok, (ix + 0.5) / Wf, torch.full_like(ix, -1e3)),
+                           torch.where(ok, (iy + 0.5) / Hf, torch.full_like(iy, -1e3))], -1).permute(0, 2, 1, 3)   # [B,Q,V,2]
+        value = mod.value_proj(feats.permute(0, 1, 3, 4, 2).reshape(B, V * Hf * Wf, C)).view(B, V * Hf * Wf, M, D)
+        off = mod.sampling_offsets(query).view(B, Q, M, V, P, 2)
+        loc = ref.view(B, Q, 1, V, 1, 2) + off / torch.tensor([Wf, Hf], dtype=torch.float32)
+        aw = torch.softmax(mod.attention_weights(query).view(B, Q, M, V * P), -1).view(B, Q, M, V, P)
+        smp = dorc.deform_attn_grid_sample(value, [(Hf, Wf)] * V, loc, aw)
+        want = mod.output_proj(smp).view(B, bhw[0], bhw[1], C).permute(0, 3, 1, 2)
+    assert float((out - want).abs().max()) <= 3e-4 * float(want.abs().max())
+
+
+@pytest.mark.gpu
+def test_image_space_fusion_trains():
+    import bevipm
+    from bevipm import rig
+    torch.manual_seed(0)
+    B, V, C = 1, 3, 32
+    K, Rt = _rig(B, V)
+    mod = bevipm.ImageSpaceDeformAttnFusion(10, 14, rig.WILDTRACK_BOUNDS, C, V, heads=4, points=2).cuda()
+    with torch.no_grad():
+        mod.attention_weights.weight.normal_(0, 0.02)
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+    x = torch.randn(B, V, C, 12, 20, device="cuda", requires_grad=True)
+    y = mod(x, K, Rt, img_size=rig.WILDTRACK_IMG_SIZE)
+    assert y.shape == (B, C, 10, 14)
+    y.square().mean().backward()
+    assert x.grad is not None and float(x.grad.abs().max()) > 0
+    for name, prm in mod.named_parameters():
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+    assert float(mod.sampling_offsets.weight.grad.abs().max()) > 0 and float(mod.attention_weights.weight.grad.abs().max()) > 0

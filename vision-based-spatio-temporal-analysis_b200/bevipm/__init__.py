@@ -3,9 +3,9 @@ project/models/fusion/{geometry,fusion}.py).  CUDA only: importing the product p
 libbevipm.so raises."""
 from . import rig  # host-side synthetic inputs; no GPU needed
 from .modules import (AttentionFusion, ConcatFusion, DeformAttnFusion, FoldedConcatProjIPM, FusedIPM, FusionModule, GeometryTransformer,
-                      SimpleFusion,
+                      ImageSpaceDeformAttnFusion, SimpleFusion,
                       pack_calibration)
 from . import ops, sharding
 
-__all__ = ["GeometryTransformer", "FusedIPM", "FoldedConcatProjIPM", "FusionModule", "SimpleFusion", "ConcatFusion", "AttentionFusion", "DeformAttnFusion",
+__all__ = ["GeometryTransformer", "FusedIPM", "FoldedConcatProjIPM", "FusionModule", "SimpleFusion", "ConcatFusion", "AttentionFusion", "DeformAttnFusion", "ImageSpaceDeformAttnFusion",
            "pack_calibration", "ops", "rig", "sharding"]

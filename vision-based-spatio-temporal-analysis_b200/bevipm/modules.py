@@ -457,3 +457,94 @@ class DeformAttnFusion(FusionModule):
         out = ops.deform_attn(value, shapes, start, loc, aw, out_dtype=value.dtype)  # [B,Q,C]
         out = self.output_proj(out.to(query.dtype))
         return out.view(B, H, W, C).permute(0, 3, 1, 2)
+
+
+class ImageSpaceDeformAttnFusion(_IPMBase):
+    """Phase-2 fusion WITHOUT the per-view BEV maps: every BEV cell is a query that samples the SOURCE feature maps of all
+    views around the cell's own inverse-perspective position (the fused, image-space form of DeformAttnFusion).
+
+    forward(feats [B,V,C,Hf,Wf], intrinsics, extrinsics, img_size) -> [B,C,Hb,Wb] -- GeometryTransformer's signature, so it
+    replaces `geom` + `fusion` of BEVNet together (model_wrapper.py:68-69) like FusedIPM does.
+      reference point of cell q in view v = the position the reference's warp samples (geometry.py:142-160; our
+        `bevipm_sample_coords`), as a normalised location of the deformable-attention kernel;
+      query = the mean-fused BEV of the fused warp kernel; learned offsets are in SOURCE texels (per head / view / point);
+      value = value_proj(features) on the source maps (V*Hf*Wf texels: never warped, never materialised on the BEV grid);
+      weights: softmax over views x points per head; `mask_invalid=True` takes the softmax over the views that see the cell
+        only (the attention counterpart of fusion="mean_valid"); the default keeps every view, a view that misses the cell
+        contributes its zero padding like in the reference's mean (fusion.py:20-21).
+    With zero offsets, uniform weights and identity projections the result IS the reference's GeometryTransformer ->
+    SimpleFusion('mean') (tests/test_deform_attn.py pins the module to the fused kernel that way).  Forward and backward run on
+    our kernels (bevipm_warp_fuse_*, bevipm_sample_coords, bevipm_deform_attn_*); the projections are nn.Linear.
+    """
+
+    def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, channels: int, views: int, heads: int = 8, points: int = 4,
+                 mask_invalid: bool = False):
+        super().__init__(bev_h, bev_w, bev_bounds)
+        assert channels % heads == 0
+        self.channels, self.views, self.heads, self.points = channels, views, heads, points
+        self.mask_invalid = mask_invalid
+        self.sampling_offsets = nn.Linear(channels, heads * views * points * 2)
+        self.attention_weights = nn.Linear(channels, heads * views * points)
+        self.value_proj = nn.Linear(channels, channels)
+        self.output_proj = nn.Linear(channels, channels)
+        nn.init.zeros_(self.sampling_offsets.weight)
+        import math
+        th = torch.arange(heads, dtype=torch.float32) * (2.0 * math.pi / heads)
+        grid = torch.stack([th.cos(), th.sin()], -1)
+        grid = (grid / grid.abs().max(-1, keepdim=True)[0]).view(heads, 1, 1, 2).repeat(1, views, points, 1)
+        for i in range(points):
+            grid[:, :, i, :] *= i + 1
+        with torch.no_grad():
+            self.sampling_offsets.bias.copy_(grid.reshape(-1))
+        nn.init.zeros_(self.attention_weights.weight)
+        nn.init.zeros_(self.attention_weights.bias)
+
+    def reference_points(self, K: torch.Tensor, Rt: torch.Tensor, feat_hw, img_size):
+        """loc [B,Q,V,2] (x, y in [0,1] of each view's map; far outside where the position is not finite) and seen [B,Q,V]."""
+        Hf, Wf = feat_hw
+        xs, ys = self._ground_axes(K.device)
+        ix, iy = ops.sample_coords(K, Rt, xs, ys, (Hf, Wf), img_size)                       # [B,V,Hb,Wb], source texel units
+        ok = torch.isfinite(ix) & torch.isfinite(iy)
+        seen = ok & (ix > -1) & (ix < Wf) & (iy > -1) & (iy < Hf)                           # some tap of the cell is in the map
+        lx = torch.where(ok, (ix + 0.5) / Wf, torch.full_like(ix, -1e3))
+        ly = torch.where(ok, (iy + 0.5) / Hf, torch.full_like(iy, -1e3))
+        B, V = ix.shape[:2]
+        loc = torch.stack([lx, ly], -1).view(B, V, -1, 2).permute(0, 2, 1, 3)                # [B,Q,V,2]
+        return loc, seen.view(B, V, -1).permute(0, 2, 1)
+
+    def forward(self, feats: torch.Tensor, intrinsics, extrinsics, img_size: Tuple[int, int] = (1080, 1920)) -> torch.Tensor:
+        if feats.dim() != 5:
+            raise ValueError("feats must be [B,V,C,Hf,Wf]")
+        if not feats.is_cuda:
+            raise RuntimeError("bevipm runs on CUDA tensors only: there is no CPU implementation of this path")
+        B, V, C, Hf, Wf = feats.shape
+        assert V == self.views and C == self.channels
+        M, P, D = self.heads, self.points, C // self.heads
+        Hb, Wb = self.bev_h, self.bev_w
+        Q = Hb * Wb
+        if feats.dtype == torch.float16:
+            feats = feats.float()
+        feats = ops.to_channels_last5(feats)                                               # [B,V,Hf,Wf,C] in memory
+        K, Rt = pack_calibration(intrinsics, extrinsics, B, V, feats.device)
+        bev = self._run(feats, K, Rt, img_size, _lib.MEAN, False, 0, "keep")               # fused warp + mean: the query
+        query = bev.permute(0, 2, 3, 1).reshape(B, Q, C).to(self.value_proj.weight.dtype)
+        with torch.no_grad():
+            ref, seen = self.reference_points(K, Rt, (Hf, Wf), img_size)
+        src = feats.permute(0, 1, 3, 4, 2).reshape(B, V * Hf * Wf, C)
+        value = self.value_proj(src.to(self.value_proj.weight.dtype)).view(B, V * Hf * Wf, M, D)
+        off = self.sampling_offsets(query).view(B, Q, M, V, P, 2)
+        loc = ref.view(B, Q, 1, V, 1, 2).to(off.dtype) + off / torch.tensor([Wf, Hf], device=off.device, dtype=off.dtype)
+        logits = self.attention_weights(query).view(B, Q, M, V, P)
+        if self.mask_invalid:
+            logits = logits.masked_fill(~seen.view(B, Q, 1, V, 1), float("-inf"))
+            aw = torch.softmax(logits.reshape(B, Q, M, V * P), -1)
+            aw = torch.nan_to_num(aw, nan=0.0).view(B, Q, M, V, P)                          # cells no view sees: all weights 0
+        else:
+            aw = torch.softmax(logits.reshape(B, Q, M, V * P), -1).view(B, Q, M, V, P)
+        shapes = torch.tensor([[Hf, Wf]] * V, dtype=torch.int32, device=feats.device)
+        start = torch.arange(V, device=feats.device, dtype=torch.int64) * (Hf * Wf)
+        if value.dtype not in (torch.float32, torch.bfloat16):
+            value = value.float()
+        out = ops.deform_attn(value, shapes, start, loc, aw, out_dtype=value.dtype)         # [B,Q,C]
+        out = self.output_proj(out.to(query.dtype))
+        return out.view(B, Hb, Wb, C).permute(0, 3, 1, 2)
