@@ -401,6 +401,63 @@ def batch1_latency_block(dev):
     return res
 
 
+def folded_proj_block(dev, peak: float):
+    """BEVNet's 1x1 projection folded in front of the warp at wildtrack.yaml's shape: the per-view GEMM
+    [7 x 135*240, 1280] x [1280, 128] on the library's tcgen05 kernel (one TF32 pass, and split operands = fp32-grade) beside
+    cuBLAS (torch.einsum), and the whole FoldedConcatProjIPM forward.  Informational: outside every timed region."""
+    import torch
+    import bevipm
+    from bevipm import ops, rig
+    V, C, Co, fhw, bhw = 7, 1280, 128, (135, 240), (120, 360)
+    g = torch.Generator(device=dev).manual_seed(4)
+    xs = [torch.randn(V, fhw[0] * fhw[1], C, device=dev, generator=g) for _ in range(3)]   # 3 x 1.16 GB: every launch reads cold inputs
+    W = torch.randn(Co, V, C, device=dev, generator=g) / C ** 0.5
+    alg = xs[0].numel() * 4 + W.numel() * 4 + V * fhw[0] * fhw[1] * Co * 4
+
+    def timed(fn, n=30):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / n
+
+    want = torch.einsum("vrc,ovc->vro", xs[0][:, :2048].double(), W.double())
+    res = {"workload": "wildtrack.yaml projection: 7 views x 1280 ch x 135x240 fp32 -> 128 ch (per-view GEMM on the source maps)",
+           "algorithmic_bytes": alg, "gemm": {}}
+    prev = torch.backends.cuda.matmul.allow_tf32
+    for name, fn, tf32 in (("ours_tcgen05_tf32", lambda i: ops.proj1x1(xs[i % 3], W, 1), False),
+                           ("ours_tcgen05_split3_fp32_grade", lambda i: ops.proj1x1(xs[i % 3], W, 3), False),
+                           ("cublas_tf32", lambda i: torch.einsum("vrc,ovc->vro", xs[i % 3], W), True),
+                           ("cublas_fp32", lambda i: torch.einsum("vrc,ovc->vro", xs[i % 3], W), False)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        ms = timed(fn)
+        err = float((fn(0)[:, :2048].double() - want).abs().max() / want.abs().max())
+        res["gemm"][name] = {"ms": ms, "algorithmic_gbs": alg / ms / 1e6, "frac_of_measured_hbm": alg / ms / 1e6 / peak,
+                             "tflops": 2.0 * V * fhw[0] * fhw[1] * C * Co / ms / 1e9, "max_rel_err_vs_float64": err}
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del xs
+    torch.cuda.empty_cache()
+    K, Rt = rig.look_at_rig(V, 0)
+    K, Rt = K[None].to(dev), Rt[None].to(dev)
+    feats = [torch.randn(1, V, *fhw, C, device=dev, generator=g).permute(0, 1, 4, 2, 3) for _ in range(2)]
+    proj = torch.nn.Conv2d(V * C, Co, 1).to(dev)
+    with torch.no_grad():
+        for name, kw in (("folded_ours_fp32_grade", dict(precision="fp32", gemm="tcgen05")), ("folded_ours_tf32", dict(precision="tf32", gemm="tcgen05")),
+                         ("folded_cublas_fp32", dict(gemm="cublas"))):
+            m = bevipm.FoldedConcatProjIPM(*bhw, rig.WILDTRACK_BOUNDS, proj, views=V, **kw).to(dev)
+            res.setdefault("module_forward_ms_per_frame", {})[name] = timed(lambda i: m(feats[i & 1], K, Rt, img_size=rig.WILDTRACK_IMG_SIZE), 20)
+        geom = bevipm.GeometryTransformer(*bhw, rig.WILDTRACK_BOUNDS, warp_impl="grid_sample").to(dev)
+        cat = bevipm.ConcatFusion()
+        res["module_forward_ms_per_frame"]["unfolded_warp_concat_conv_cudnn_default"] = timed(
+            lambda i: proj(cat(geom(feats[i & 1], K, Rt, img_size=rig.WILDTRACK_IMG_SIZE))), 10)
+    return res
+
+
 def view_sharded_block(dev, world: int, rank: int, steps: int = 30):
     """BASELINE configs[2]: c3 (7 views x 128 ch fp32 270x480 -> 480x1440 BEV), the cameras of ONE frame split over the
     ranks.  compute_only = every rank warps its cameras into a partial sum, no exchange; then the three exchange forms of
@@ -724,6 +781,12 @@ def run_ours(args, wl):
                 extras["batch1_latency"] = batch1_latency_block(dev)
             except Exception as e:
                 extras["batch1_latency"] = {"error": repr(e)[:200]}
+            try:
+                del feats, out
+                torch.cuda.empty_cache()
+                extras["folded_proj"] = folded_proj_block(dev, peak0)
+            except Exception as e:
+                extras["folded_proj"] = {"error": repr(e)[:200]}
         else:
             try:
                 del feats, out
@@ -764,7 +827,7 @@ def run_ours(args, wl):
             line["roofline"]["sustained_frac"] = extras["sustained"]["frac"]
             line["roofline"]["sustained_ms_per_step"] = extras["sustained"]["ms_per_step"]
             line["roofline"]["sustained_launches"] = extras["sustained"]["launches"]
-        for k in ("torch_gpu_chain", "batch1_latency", "view_sharded"):
+        for k in ("torch_gpu_chain", "batch1_latency", "view_sharded", "folded_proj"):
             if k in extras:
                 line[k] = extras[k]
         if e2e:

@@ -257,6 +257,23 @@ def test_run_kernel_non_finite_features_on_the_map_border_match_the_reference_ex
         assert _same(out, want), mode
 
 
+@pytest.mark.parametrize("ksplit", ["1", "2"])
+@pytest.mark.parametrize("C,dtype", [(512, torch.float32), (384, torch.float32), (132, torch.float32), (512, torch.bfloat16), (264, torch.bfloat16)])
+def test_run_kernel_one_or_two_warps_per_row_segment(monkeypatch, ksplit, C, dtype):
+    """The default sum / mean kernel runs with one warp per row segment (large grids) or two that share the segment's tables
+    and take every other 512-byte chunk (small grids, csrc/bevipm_run.cu pick_ksplit): both forms, forced through the
+    development switch, on whole, odd and partial chunk counts, with a calibration change inside the frame group."""
+    monkeypatch.setenv("BEVIPM_RUN_KSPLIT", ksplit)
+    feats, K, Rt, xs, ys, img = _rig_case(3, 5, C, (31, 53), (37, 91), seed=17)
+    K, Rt = K.copy(), Rt.copy()
+    K[2, :, 0, 0] *= 1.03                      # frame 2 has its own calibration
+    f = torch.from_numpy(feats).to(dtype).float().numpy()
+    for mode in ("mean", "sum"):
+        want = orc.warp_fuse(f, K, Rt, xs, ys, img, mode)
+        out = _run(f, K, Rt, xs, ys, img, mode, True, dtype=dtype).cpu().numpy()
+        assert _same(out, want), (mode, ksplit)
+
+
 @pytest.mark.parametrize("seed", range(12))
 def test_default_dispatch_random_shapes(seed):
     """Whatever kernel the library picks (variant 0) for a random shape and mode must equal the oracle: whole and
