@@ -28,8 +28,12 @@ int pick_ksplit(const FwdParams& p, int maxreg) {
 
 template <typename TIn, typename TOut>
 int launch_typed(const FwdParams& p, int kmode, int maxreg, cudaStream_t st) {
-    if (kmode == KM_MAX) return launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, KM_MAX>(p, st);
-    if (kmode == KM_NONE) return launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, KM_NONE>(p, st);
+    if (kmode == KM_MAX)
+        return pick_ksplit<TIn>(p, 128) == 2 ? launch_run<TIn, TOut, 8, 4, 2, 128, 4, false, 0, KM_MAX>(p, st)
+                                             : launch_run<TIn, TOut, 8, 4, 1, 128, 4, false, 0, KM_MAX>(p, st);
+    if (kmode == KM_NONE)
+        return pick_ksplit<TIn>(p, 96) == 2 ? launch_run<TIn, TOut, 8, 4, 2, 96, 4, false, 0, KM_NONE>(p, st)
+                                            : launch_run<TIn, TOut, 8, 4, 1, 96, 4, false, 0, KM_NONE>(p, st);
     const int ks = pick_ksplit<TIn>(p, maxreg <= 96 ? 96 : 128);
     if (maxreg <= 96) return ks == 2 ? launch_run<TIn, TOut, 8, 4, 2, 96, 4, false>(p, st) : launch_run<TIn, TOut, 8, 4, 1, 96, 4, false>(p, st);
     return ks == 2 ? launch_run<TIn, TOut, 8, 4, 2, 128, 4, false>(p, st) : launch_run<TIn, TOut, 8, 4, 1, 128, 4, false>(p, st);
