@@ -62,7 +62,10 @@ def _proj_case(BV, V, rows, C, Co, seed=0):
     (2, 1, 128, 32, 32),              # exactly one tile, one k-block
     (4, 2, 129, 36, 48),              # one row past a tile; C not a multiple of the k-block (zero-filled by the copy engine)
     (1, 1, 77, 4, 256),               # a single map (extent-1 outer dimension), widest N, one partial k-block
-    (5, 5, 300, 520, 240),            # N not a power of two, 1 CTA per SM
+    (5, 5, 300, 520, 240),            # N not a power of two
+    (3, 3, 129, 64, 128),             # transposed form: a pair and a single per map (2 units), second unit one row
+    (2, 2, 128 * 5 + 17, 96, 128),    # transposed form: odd number of units per map, ragged last unit
+    (1, 1, 100, 32, 128),             # transposed form: a single unit smaller than its box
     (3, 3, 4099, 64, 80),             # N = 80: the last 32-column store is clipped at 80
 ])
 @pytest.mark.parametrize("passes", [3, 1])

@@ -109,6 +109,8 @@ def variant_name(v: int) -> str:
         return f"warp_fuse_run_kernel (variant {v})"
     if v == 55:
         return "warp_fuse_boxrun_kernel (run kernel, ring filled by TMA 2x2 box copies, variant 55)"
+    if v == 71:
+        return "proj1x1_t_kernel (tcgen05 TF32 GEMM of the folded 1x1 projection, transposed form for 128 output channels, variant 71)"
     if v == 70:
         return "proj1x1_tf32_kernel (tcgen05 TF32 GEMM of the folded 1x1 projection, variant 70)"
     if v == 60:
