@@ -179,6 +179,26 @@ int bevipm_deform_attn_bwd(const bevipm_deform_desc *d, const void *value, const
                            float *grad_value, float *grad_loc, float *grad_attn, void *stream);
 
 /*
+ * Table cache across launches ("cache per-camera coefficient tables / precomputed tap indices + weights";
+ * the `_grid_cache` the reference declares and never fills, geometry.py:22).  Cameras are static (wildtrack_loader.py:291-293
+ * reads one calibration per camera), so everything the fused kernel derives from the calibration -- per row segment: the blend
+ * weights of every (view, cell), the tap offsets of every 2x2 block the row enters, the views that see it -- can be kept on the
+ * device between calls.  `plan` is a caller-owned device buffer of bevipm_plan_bytes(d) bytes, ZEROED before its first use
+ * (cudaMemset; zeroing it again re-arms it).  bevipm_warp_fuse_fwd_planned is bevipm_warp_fuse_fwd for launches that take the
+ * default run kernel (channels-last, V <= 32, d->variant == 0; anything else: BEVIPM_ERR_UNSUPPORTED, use the plain entry):
+ *   - an empty cache is filled by the first launch from ITS FRAME 0 (tables written by the CTAs that build them, the header --
+ *     calibration, shapes / strides / axes key -- published by the last of them);
+ *   - afterwards every frame whose K and Rt34 equal the cached calibration BIT FOR BIT (compared on the device, per CTA,
+ *     together with the ends of xs / ys) copies its tables from the cache instead of computing them; any other frame computes
+ *     them as before.  The result is identical to bevipm_warp_fuse_fwd in every case; only the time differs.
+ * A cache is bound to the first calibration it sees and to one stream at a time.  Config 2 (one 128-channel chunk per texel,
+ * where the table build is 31 % of the kernel's instructions): see DESIGN.md 5.
+ */
+int64_t bevipm_plan_bytes(const bevipm_desc *d);
+int bevipm_warp_fuse_fwd_planned(const bevipm_desc *d, const void *feats, const float *K, const float *Rt34, const float *xs,
+                                 const float *ys, void *out, void *plan, int64_t plan_bytes, void *stream);
+
+/*
  * BEVNet's 1x1 projection folded in front of the warp.  The reference concatenates the V warped maps
  * and applies nn.Conv2d(V*C, Co, 1) on the BEV grid (model_wrapper.py:68-73); the warp is linear per channel, so
  *   proj(concat_v(warp_v(f_v))) = sum_v warp_v(W_v f_v) + bias,   W_v = proj.weight[:, v*C:(v+1)*C],

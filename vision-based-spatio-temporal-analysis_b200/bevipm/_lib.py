@@ -32,7 +32,7 @@ EXPORTS = (
     "bevipm_warp_fuse_bwd", "bevipm_sample_coords", "bevipm_nchw_to_nhwc", "bevipm_fuse_views",
     "bevipm_warp_fuse_host", "bevipm_host_release", "bevipm_deform_attn_fwd", "bevipm_last_variant", "bevipm_host_last_h2d_bytes",
     "bevipm_fuse_views_bwd", "bevipm_valid_count", "bevipm_divide_by_count", "bevipm_warp_fuse_red", "bevipm_slab_finish", "bevipm_deform_attn_bwd",
-    "bevipm_proj1x1",
+    "bevipm_proj1x1", "bevipm_plan_bytes", "bevipm_warp_fuse_fwd_planned",
 )
 
 class DeformDesc(ctypes.Structure):
@@ -77,6 +77,11 @@ def load() -> ctypes.CDLL:
     L.bevipm_deform_attn_bwd.argtypes = [ctypes.POINTER(DeformDesc), vp, vp, vp, fp, fp, vp, fp, fp, fp, vp]
     L.bevipm_deform_attn_bwd.restype = ctypes.c_int
     i32, i64 = ctypes.c_int32, ctypes.c_int64
+    if hasattr(L, "bevipm_plan_bytes"):
+        L.bevipm_plan_bytes.argtypes = [dp]
+        L.bevipm_plan_bytes.restype = ctypes.c_int64
+        L.bevipm_warp_fuse_fwd_planned.argtypes = [dp, vp, fp, fp, fp, fp, vp, vp, ctypes.c_int64, vp]
+        L.bevipm_warp_fuse_fwd_planned.restype = ctypes.c_int
     if hasattr(L, "bevipm_proj1x1"):   # (absent only from an older build loaded through BEVIPM_LIB for an A/B)
         L.bevipm_proj1x1.argtypes = [fp, fp, fp, fp, i32, i32, i64, i32, i32, i64, i64, i64, i64, i32, vp]
         L.bevipm_proj1x1.restype = ctypes.c_int

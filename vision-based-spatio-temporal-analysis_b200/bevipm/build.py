@@ -39,12 +39,23 @@ def _obj(src: Path) -> Path:
     return OBJ / (src.stem + ".o")
 
 
+def _src_mtime(src: Path) -> float:
+    """A source's own time stamp, or that of a .cu it includes (bevipm_run_plan.cu compiles bevipm_run.cu a second time)."""
+    t = src.stat().st_mtime
+    for line in src.read_text().splitlines():
+        if line.startswith('#include "') and line.rstrip().endswith('.cu"'):
+            inc = CSRC / line.split('"')[1]
+            if inc.exists():
+                t = max(t, inc.stat().st_mtime)
+    return t
+
+
 def _stale_objects():
     hm = _headers_mtime()
     out = []
     for s in sources():
         o = _obj(s)
-        if not o.exists() or o.stat().st_mtime < max(s.stat().st_mtime, hm):
+        if not o.exists() or o.stat().st_mtime < max(_src_mtime(s), hm):
             out.append(s)
     return out
 

@@ -113,6 +113,11 @@ class _IPMBase(nn.Module):
         self.res_y = (bev_bounds[3] - bev_bounds[2]) / bev_h
         self.register_buffer("ground_grid", self._create_ground_grid(), persistent=False)
         self._axes = {}
+        # static cameras (wildtrack_loader.py:291-293): keep the calibration-derived tables of the fused kernel on the device
+        # between calls -- the `_grid_cache` the reference declares and never fills (geometry.py:22).  Opt-in (subclasses take
+        # `cache_tables=True`); results are identical either way, the kernel verifies the calibration on the device.
+        self.cache_tables = False
+        self._plans = {}
 
     def _create_ground_grid(self) -> torch.Tensor:
         # geometry.py:24-31 -- the linspace values themselves are part of the contract (rig.ground_axes)
@@ -161,7 +166,19 @@ class _IPMBase(nn.Module):
         if layout == "channels_last" or (layout == "auto" and feats.shape[2] % (4 if feats.dtype == torch.float32 else 8) == 0):
             feats = ops.to_channels_last5(feats)
         H_img, W_img = img_size
+        if self.cache_tables and variant == 0 and ops.planned_ok(feats):
+            key = (str(feats.device), feats.dtype, tuple(feats.shape[1:]), tuple(feats.stride()[1:]), int(mode), int(H_img), int(W_img))
+            plan = self._plans.get(key)
+            if plan is None:
+                plan = self._plans[key] = ops.new_plan(V, (self.bev_h, self.bev_w), feats.device)
+            return ops.warp_fuse_planned(feats, K, Rt, xs, ys, int(H_img), int(W_img), mode, out_bf16, plan)
         return ops.warp_fuse(feats, K, Rt, xs, ys, int(H_img), int(W_img), mode, out_bf16, variant)
+
+    def reset_table_cache(self) -> None:
+        """Forget the cached tables (call after the cameras moved: a cache is bound to the first calibration it sees; until
+        then frames with another calibration are still computed correctly, just without the cache)."""
+        for plan in self._plans.values():
+            plan.zero_()
 
 
     def _kornia_singular(self, K, Rt34, feat_hw, img_size) -> torch.Tensor:
@@ -202,8 +219,9 @@ class GeometryTransformer(_IPMBase):
     """Per-view IPM warp, drop-in for geometry.py:12-163 (grid_sample semantics)."""
 
     def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, warp_impl: str = "grid_sample", layout: str = "keep",
-                 emulate_kornia: bool | None = None):
+                 emulate_kornia: bool | None = None, cache_tables: bool = False):
         super().__init__(bev_h, bev_w, bev_bounds)
+        self.cache_tables = cache_tables
         # geometry.py:20 -- both names are accepted; 'kornia' executes the grid_sample branch in any
         # environment without kornia (this image) and the kornia branch where kornia imports: emulate_kornia=None
         # (default) mirrors exactly that decision (_resolve_kornia).  The kornia-compatible mode reproduces the sample
@@ -251,8 +269,10 @@ class FusedIPM(_IPMBase):
 
     def __init__(self, bev_h: int, bev_w: int, bev_bounds: tuple, fusion: str = "mean",
                  warp_impl: str = "grid_sample", out_dtype: torch.dtype = torch.float32,
-                 layout: str = "auto", variant: int = 0, emulate_kornia: bool | None = None, return_valid: bool = False):
+                 layout: str = "auto", variant: int = 0, emulate_kornia: bool | None = None, return_valid: bool = False,
+                 cache_tables: bool = False):
         super().__init__(bev_h, bev_w, bev_bounds)
+        self.cache_tables = cache_tables   # static cameras: keep the calibration-derived tables on the device between calls
         # "mean_valid": mean over the views that SEE a cell (opt-in extension; the reference's "mean" divides by V)
         assert fusion in ("sum", "mean", "max", "concat", "none", "mean_valid")
         assert out_dtype in (torch.float32, torch.bfloat16)

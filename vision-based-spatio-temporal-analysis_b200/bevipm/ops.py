@@ -164,6 +164,79 @@ def _backward(ctx, grad_out):
 warp_fuse.register_autograd(_backward, setup_context=_setup_ctx)
 
 
+# ---- the same op over a table cache (static cameras: SURVEY.md 8(f) N4, the reference's unused `_grid_cache`) --------
+
+def plan_bytes(V: int, bev_hw: Tuple[int, int]) -> int:
+    """Bytes of a table cache for V views and a [Hb, Wb] grid (include/bevipm.h: bevipm_plan_bytes)."""
+    d = _fill_desc((1, V, 8, 2, 2), (0,) * 5, (0,) * 5, bev_hw, (2, 2), 0, 0, 0, 0)
+    n = int(_lib.load().bevipm_plan_bytes(ctypes.byref(d)))
+    if n < 0:
+        raise RuntimeError(_lib.load().bevipm_last_error().decode())
+    return n
+
+
+def new_plan(V: int, bev_hw: Tuple[int, int], device) -> torch.Tensor:
+    """An empty (zeroed) table cache; `plan.zero_()` re-arms it for another calibration."""
+    return torch.zeros(plan_bytes(V, bev_hw), dtype=torch.uint8, device=device)
+
+
+# (`plan` is declared read-only although the first call fills it: a cache whose content never changes the result is not a
+#  mutation the dispatcher has to order anything around, and a functional schema is what autograd registration needs)
+@torch.library.custom_op("bevipm::warp_fuse_planned", mutates_args=(), device_types="cuda")
+def warp_fuse_planned(feats: torch.Tensor, K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,
+                      img_h: int, img_w: int, mode: int, out_bf16: bool, plan: torch.Tensor) -> torch.Tensor:
+    """warp_fuse for launches that take the default run kernel (channels-last features, V <= 32), with the calibration-
+    derived tables of every row segment kept in `plan` between calls: the first call fills an empty cache from its frame 0,
+    later frames with the same calibration (compared on the device, bit for bit) copy their tables instead of computing
+    them.  The result equals warp_fuse's bit for bit in every case."""
+    if feats.dim() != 5:
+        raise ValueError("feats must be [B,V,C,Hf,Wf]")
+    if feats.dtype not in _DT:
+        raise TypeError(f"feats dtype {feats.dtype} is not supported (float32 / bfloat16)")
+    _check_calib(feats, K, Rt34, xs, ys)
+    if plan.dtype != torch.uint8 or not plan.is_contiguous() or plan.device != feats.device:
+        raise ValueError("plan must be a contiguous uint8 tensor on the features' device (ops.new_plan)")
+    L = _lib.load()
+    mode, flags = mode & 0xff, mode >> 8
+    per_view = mode == _lib.NONE
+    Hb, Wb = ys.numel(), xs.numel()
+    out_dtype = torch.bfloat16 if out_bf16 else torch.float32
+    with torch.cuda.device(feats.device):
+        out = _alloc_out(feats, Hb, Wb, per_view, out_dtype, _is_channels_last5(feats))
+        d = _fill_desc(feats.shape, feats.stride(), _out_strides5(out, per_view), (Hb, Wb), (img_h, img_w), mode,
+                       _DT[feats.dtype], _DT[out_dtype], 0, flags)
+        _lib.check(L.bevipm_warp_fuse_fwd_planned(ctypes.byref(d), _ptr(feats), _ptr(K), _ptr(Rt34), _ptr(xs), _ptr(ys),
+                                                  _ptr(out), _ptr(plan), plan.numel(), ctypes.c_void_p(_stream_ptr(feats.device))))
+    return out
+
+
+@warp_fuse_planned.register_fake
+def _(feats, K, Rt34, xs, ys, img_h, img_w, mode, out_bf16, plan):
+    B, V, C = feats.shape[:3]
+    Hb, Wb = ys.numel(), xs.numel()
+    dt = torch.bfloat16 if out_bf16 else torch.float32
+    per_view = (mode & 0xff) == _lib.NONE
+    if _is_channels_last5(feats):
+        if per_view:
+            return feats.new_empty((B, V, Hb, Wb, C), dtype=dt).permute(0, 1, 4, 2, 3)
+        return feats.new_empty((B, Hb, Wb, C), dtype=dt).permute(0, 3, 1, 2)
+    return feats.new_empty((B, V, C, Hb, Wb) if per_view else (B, C, Hb, Wb), dtype=dt)
+
+
+def _setup_ctx_planned(ctx, inputs, output):
+    _setup_ctx(ctx, inputs[:9] + (0,), output)
+
+
+warp_fuse_planned.register_autograd(_backward, setup_context=_setup_ctx_planned)
+
+
+def planned_ok(feats: torch.Tensor) -> bool:
+    """Does this launch take the kernels a table cache belongs to (channels-last 16-byte vectors, V <= 32)?"""
+    ve = 4 if feats.dtype == torch.float32 else 8
+    return (feats.dim() == 5 and feats.dtype in _DT and feats.shape[1] <= 32 and _is_channels_last5(feats) and feats.shape[2] % ve == 0
+            and all(st % ve == 0 for st in (feats.stride(0), feats.stride(1), feats.stride(3), feats.stride(4))) and feats.data_ptr() % 16 == 0)
+
+
 # ---- the remaining entry points, as plain functions ----------------------------------------------
 
 def sample_coords(K: torch.Tensor, Rt34: torch.Tensor, xs: torch.Tensor, ys: torch.Tensor,

@@ -74,6 +74,8 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
     for (int q = 0; q < 16; ++q) p.slab[q] = nullptr;
     p.slab_rows = 1;
     p.slab_put = 0;
+    p.plan = nullptr;
+    p.plan_key = 0;
     if (d->flags & BEVIPM_FLAG_KORNIA_GEOMETRY) {
         p.kx = d->Wf > 1 ? (float)((double)d->Wf / (double)(d->Wf - 1)) : 1.0f;
         p.ky = d->Hf > 1 ? (float)((double)d->Hf / (double)(d->Hf - 1)) : 1.0f;
@@ -82,6 +84,13 @@ FwdParams make_params(const bevipm_desc* d, const void* feats, const float* K, c
 }
 
 int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
+    return h;
+}
+
 
 // ---- fused NHWC fast path ---------------------------------------------------------------------
 // variant ids (bevipm_desc.variant); 0 = auto.  1..10 tile kernel shapes, 11..14 its loads-only timing probes,
@@ -382,6 +391,39 @@ int bevipm_warp_fuse_fwd(const bevipm_desc* d, const void* feats, const float* K
     return launch_strided<__nv_bfloat16, __nv_bfloat16>(p, st);
 }
 
+int64_t bevipm_plan_bytes(const bevipm_desc* d) {
+    if (check_desc(d)) return -1;
+    if (d->V > bevipm::kRunMaxViews) { fail(BEVIPM_ERR_UNSUPPORTED, "table cache: V = %d (at most %d)", d->V, bevipm::kRunMaxViews); return -1; }
+    return (int64_t)bevipm::run_plan_bytes(d->V, d->Hb, d->Wb);
+}
+
+int bevipm_warp_fuse_fwd_planned(const bevipm_desc* d, const void* feats, const float* K, const float* Rt34, const float* xs,
+                                 const float* ys, void* out, void* plan, int64_t plan_bytes, void* stream) {
+    if (int rc = check_desc(d)) return rc;
+    if (!feats || !K || !Rt34 || !xs || !ys || !out || !plan) return fail(BEVIPM_ERR_BAD_ARG, "null device pointer");
+    if (d->variant != 0) return fail(BEVIPM_ERR_BAD_ARG, "the table cache belongs to the default kernels: variant must be 0, got %d", d->variant);
+    if (plan_bytes < (int64_t)bevipm::run_plan_bytes(d->V, d->Hb, d->Wb) || (reinterpret_cast<uintptr_t>(plan) & 15))
+        return fail(BEVIPM_ERR_BAD_ARG, "table cache: %lld bytes given, %lld needed (16-byte aligned)", (long long)plan_bytes,
+                    (long long)bevipm::run_plan_bytes(d->V, d->Hb, d->Wb));
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    FwdParams p = make_params(d, feats, K, Rt34, xs, ys, out);
+    const bool in32 = d->in_dtype == BEVIPM_F32, out32 = d->out_dtype == BEVIPM_F32;
+    const bool ok = fast_path_ok(d, feats, out) && (in32 ? run_kernel_ok<float>(p) : run_kernel_ok<__nv_bfloat16>(p)) && !(in32 && !out32);
+    if (!ok) return fail(BEVIPM_ERR_UNSUPPORTED, "table cache: this launch does not take the run kernel (channels-last, V <= %d, 32-bit tap offsets)", bevipm::kRunMaxViews);
+    // everything the tables depend on besides the calibration (which the kernel compares itself, with the ends of the axes)
+    const int ve = in32 ? 4 : 8;
+    const int64_t parts[] = {d->V, d->Hf, d->Wf, d->Hb, d->Wb, d->img_h, d->img_w, d->flags & BEVIPM_FLAG_KORNIA_GEOMETRY,
+                             d->fs_v / ve, d->fs_y / ve, d->fs_x / ve, d->mode == BEVIPM_MAX ? 1 : 0, /* layout version */ 1};
+    uint64_t key = fnv1a(1469598103934665603ULL, parts, sizeof(parts));
+    if (key == 0) key = 1;
+    p.plan = plan;
+    p.plan_key = key;
+    const int kmode = d->mode == BEVIPM_MAX ? bevipm::KM_MAX : (d->mode == BEVIPM_NONE ? bevipm::KM_NONE : bevipm::KM_ACC);
+    const int maxreg = (kmode == bevipm::KM_ACC && in32) || kmode == bevipm::KM_NONE ? 96 : 128;
+    g_last_variant = in32 ? 32 : 33;
+    return bevipm::launch_run_planned(p, !in32, !out32, kmode, maxreg, st);
+}
+
 int bevipm_warp_fuse_bwd(const bevipm_desc* d, const void* grad_out, const float* K, const float* Rt34, const float* xs,
                          const float* ys, float* grad_feats, void* stream) {
     using namespace bevipm;
@@ -621,11 +663,6 @@ struct HostArena {
 thread_local HostArena g_arena;
 thread_local int64_t g_host_h2d_bytes = 0;
 
-uint64_t fnv1a(uint64_t h, const void* data, size_t n) {
-    const unsigned char* p = static_cast<const unsigned char*>(data);
-    for (size_t i = 0; i < n; ++i) { h ^= p[i]; h *= 1099511628211ULL; }
-    return h;
-}
 
 // On any failure after copies were queued: the caller's buffers and the arena must be quiet before we return.
 struct StreamQuiet {

@@ -51,7 +51,21 @@ struct FwdParams {
     void* slab[16];
     int slab_rows;
     int slab_put;        // 0: add into the slab (bulk reduction); 1: plain bulk store (every rank has its own receive buffer at the owner)
+    // table cache across launches (run kernel, PLAN instantiations; ipm_run.cuh): a device buffer holding the phase-A tables of
+    // every row segment for ONE calibration, and the key of everything else they depend on (shapes, strides, axes, kernel shape)
+    void* plan;
+    unsigned long long plan_key;
 };
+
+// Header of a table cache (plan): 1 KB.  key == 0: empty (the first launch that finds it empty fills the tables from its frame 0
+// and its last CTA publishes the header); otherwise the tables are valid for exactly this key and this calibration, bit for bit.
+struct PlanHeader {
+    unsigned long long key;
+    unsigned int done;        // CTAs that have written their tables (reset by the publishing CTA)
+    unsigned int pad;
+    unsigned int calib[21 * 32 + 4];  // K (9 V) and Rt34 (12 V) of the calibration the tables were built from, as bit patterns
+};
+constexpr int kPlanHeaderBytes = 4096;
 
 enum { KM_ACC = 0, KM_MAX = 1, KM_NONE = 2, KM_PROBE = 3 /* timing probe: loads only, no blend */,
        KM_RED = 4 /* sum over this rank's views, ADDED (red.global.add) into the row slab of the owning rank */ };

@@ -240,6 +240,14 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     }
 }
 
+// what a table cache is compared with / filled from: K (9 V) and Rt34 (12 V) of frame b, then the ends of the two BEV axes
+__device__ __forceinline__ const float* plan_source(const FwdParams& p, int V, int b, int q) {
+    if (q < 9 * V) return p.K + (size_t)b * 9 * V + q;
+    if (q < 21 * V) return p.Rt + (size_t)b * 12 * V + (q - 9 * V);
+    q -= 21 * V;
+    return q == 0 ? p.xs : (q == 1 ? p.xs + (p.Wb - 1) : (q == 2 ? p.ys : p.ys + (p.Hb - 1)));
+}
+
 // A per-warp ring of DEPTH 2-KB stages in shared memory is filled by cp.async (.ca when CA, else .cg), DEPTH-1
 // blocks in flight per warp; every lane reads back exactly the 16 bytes it copied, so no barrier is involved.
 // One CTA walks `fpc` consecutive frames of its tile and re-uses the phase A tables for as long as the
@@ -251,7 +259,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 // KM_NONE = the per-view maps GeometryTransformer returns (geometry.py:162-163; what ConcatFusion reshapes): every (view, cell)
 // result is stored as soon as it is blended, zeros where a view does not see a cell; no accumulators at all.
 template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC, bool TMA = false,
-          bool HALF = false>
+          bool HALF = false, bool PLAN = false>
 __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int fpc) {
     static_assert(DEPTH >= 2 && DEPTH <= 8, "ring depth");
     static_assert(!TMA || (DEPTH & (DEPTH - 1)) == 0, "the TMA ring indexes its stages with a mask");
@@ -305,24 +313,70 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     }
 
     const int cpw = (chunks - kk + KSPLIT - 1) / KSPLIT;  // 512-byte chunks this warp walks per frame
+    bool plan_filled = false;  // PLAN: this CTA wrote its segments' tables into an empty cache
 
     for (int b = b0; b < b1;) {
         if (b > b0) __syncthreads();  // every warp is done with the previous run's tables
+        // ---- PLAN: the tables of this calibration may be waiting in the cache (static cameras: the `_grid_cache` the reference
+        // declares, geometry.py:22).  Valid iff the key matches and K, Rt34 of this frame equal the cached ones bit for bit.
+        bool use_plan = false, fill_plan = false;
+        if constexpr (PLAN) {
+            const PlanHeader* ph = reinterpret_cast<const PlanHeader*>(p.plan);
+            // the copy of this segment's cached tables starts before the header has been checked: one memory round trip instead
+            // of two (whatever an empty or foreign cache holds is overwritten by the build below)
+            if (kk == 0) {
+                const uint4* cached = reinterpret_cast<const uint4*>(static_cast<const unsigned char*>(p.plan) + kPlanHeaderBytes +
+                                                                     ((size_t)(ty * R + r) * p.tiles_x + tx) * (size_t)seg_bytes);
+                const uint32_t mine = (uint32_t)__cvta_generic_to_shared(smem_run + r * seg_bytes);
+                for (int q = lane; q < seg_bytes / 16; q += 32) cp_async16<false>(mine + q * 16, cached + q);
+                cp_async_commit();
+            }
+            const unsigned long long key = *reinterpret_cast<const volatile unsigned long long*>(&ph->key);
+            bool differs = key != p.plan_key;
+            if (!differs)
+                for (int q = tid; q < 21 * V + 4; q += NT) differs |= __float_as_uint(__ldg(plan_source(p, V, b, q))) != ph->calib[q];
+            use_plan = !__syncthreads_or(differs);
+            // an empty cache is filled from frame 0, by the CTAs that walk it (all of them see it empty: the header is published
+            // only after every one of them has finished)
+            fill_plan = __syncthreads_and(key == 0ull) && b == 0;
+            plan_filled |= fill_plan;
+            if (kk == 0) {
+                cp_async_wait<0>();
+                __syncwarp();
+            }
+        }
         // ---- the V homographies of this frame, once per CTA (geometry.py:60-63): rows padded to 4 floats ------------
         float* sH = reinterpret_cast<float*>(smem_run + run_tables_bytes(V, CELLS, R) + NW * (DEPTH * 2048));
-        if (tid < V) {
-            float H[9];
-            homography(p.K + 9 * (b * V + tid), p.Rt + 12 * (b * V + tid), H);
+        if (!use_plan) {
+            if (tid < V) {
+                float H[9];
+                homography(p.K + 9 * (b * V + tid), p.Rt + 12 * (b * V + tid), H);
 #pragma unroll
-            for (int q = 0; q < 3; ++q)
-                reinterpret_cast<float4*>(sH + 12 * tid)[q] = make_float4(H[3 * q], H[3 * q + 1], H[3 * q + 2], 0.0f);
+                for (int q = 0; q < 3; ++q)
+                    reinterpret_cast<float4*>(sH + 12 * tid)[q] = make_float4(H[3 * q], H[3 * q + 1], H[3 * q + 2], 0.0f);
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- phase A: the first warp of every row segment builds the segment's tables, directly in walking order --
         // lane = (view of this pass, cell); a ballot gives every reload its place in the load list and every view
         // that sees the segment its place in the view list (lane order = views ascending, cells ascending).
-        if (kk == 0)
-            run_build_tables<CELLS, KMODE == KM_MAX, false, HALF>(p, V, i, j0, lane, fsv16, sH, seg_wts(r), seg_loads(r), seg_meta(r));
+        if (kk == 0) {
+            if constexpr (PLAN) {
+                // this segment's tables in the cache: [header][segment (tile row ty * R + r) * tiles_x + tx] of seg_bytes each
+                uint4* cached = reinterpret_cast<uint4*>(static_cast<unsigned char*>(p.plan) + kPlanHeaderBytes +
+                                                         ((size_t)(ty * R + r) * p.tiles_x + tx) * (size_t)seg_bytes);
+                uint4* mine = reinterpret_cast<uint4*>(smem_run + r * seg_bytes);
+                if (!use_plan) {
+                    run_build_tables<CELLS, KMODE == KM_MAX, false, HALF>(p, V, i, j0, lane, fsv16, sH, seg_wts(r), seg_loads(r), seg_meta(r));
+                    if (fill_plan) {
+                        __syncwarp();
+                        for (int q = lane; q < seg_bytes / 16; q += 32) cached[q] = mine[q];
+                    }
+                }
+            } else {
+                run_build_tables<CELLS, KMODE == KM_MAX, false, HALF>(p, V, i, j0, lane, fsv16, sH, seg_wts(r), seg_loads(r), seg_meta(r));
+            }
+        }
         if (KSPLIT > 1) __syncthreads();
         else __syncwarp();
 
@@ -684,6 +738,22 @@ __global__ void __maxnreg__(MAXREG) warp_fuse_run_kernel(const FwdParams p, int 
     }
     if constexpr (KMODE == KM_RED) {
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // every bulk reduction of this warp has been performed
+    }
+    if constexpr (PLAN) {
+        // the last of the CTAs that filled an empty cache publishes its header: calibration first, key last
+        if (plan_filled) {
+            __syncthreads();
+            if (tid == 0) {
+                PlanHeader* ph = reinterpret_cast<PlanHeader*>(p.plan);
+                __threadfence();
+                if (atomicAdd(&ph->done, 1u) == gridDim.x - 1) {
+                    for (int q = 0; q < 21 * V + 4; ++q) ph->calib[q] = __float_as_uint(__ldg(plan_source(p, V, 0, q)));
+                    ph->done = 0;
+                    __threadfence();
+                    *reinterpret_cast<volatile unsigned long long*>(&ph->key) = p.plan_key;
+                }
+            }
+        }
     }
 }
 

@@ -15,6 +15,27 @@ void count_launch();                       // bevipm_api.cu: the library's launc
 
 // the default run kernels, compiled in bevipm_run.cu: kmode KM_ACC (sum / mean) at 96 or 128 registers, KM_MAX (128), KM_NONE (96)
 int launch_run_default(const FwdParams& p, bool in_bf16, bool out_bf16, int kmode, int maxreg, cudaStream_t st);
+// the same kernels reading / filling a table cache (p.plan, p.plan_key), compiled in bevipm_run_plan.cu
+int launch_run_planned(const FwdParams& p, bool in_bf16, bool out_bf16, int kmode, int maxreg, cudaStream_t st);
+// bytes of a table cache for this launch: header + one table set per row segment (rows padded to the CTA's four)
+inline size_t run_plan_bytes(int V, int Hb, int Wb) {
+    return (size_t)kPlanHeaderBytes + (size_t)((Wb + 7) / 8) * (size_t)((Hb + 3) / 4 * 4) * (size_t)run_seg_bytes(V, 8);
+}
+
+// Warps per row segment of the default kernels.  One warp per segment (it walks all channel chunks itself) has the least
+// overhead, but its CTAs are long: with fewer than ~6 waves of them the ragged end of the launch costs more than sharing a
+// segment's tables between two warps that take every other chunk (measured, fp32 512 ch = 4 chunks: 1 frame 0.0885 -> 0.0816 ms,
+// 2 frames 0.0773 -> 0.0758 per frame, 8 frames 0.0691 -> 0.0699, 64 frames 0.0715 -> 0.0722; single-chunk maps lose 45 %).
+template <typename TIn>
+int pick_ksplit(const FwdParams& p, int maxreg) {
+    if (const char* e = getenv("BEVIPM_RUN_KSPLIT")) return atoi(e) == 2 ? 2 : 1;  // development switch
+    constexpr int VE = VecTraits<TIn>::VE;
+    const int chunks = (p.C + 32 * VE - 1) / (32 * VE);
+    if (chunks < 2) return 1;
+    const long long tiles = (long long)((p.Wb + 7) / 8) * ((p.Hb + 3) / 4);
+    const long long slots = 148LL * (65536 / (maxreg * 128));
+    return tiles * p.B < 6 * slots ? 2 : 1;
+}
 
 template <typename TIn>
 bool run_kernel_ok(const FwdParams& p) {
@@ -24,7 +45,7 @@ bool run_kernel_ok(const FwdParams& p) {
 }
 
 template <typename TIn, typename TOut, int CELLS, int NW, int KSPLIT, int MAXREG, int DEPTH, bool CA, int PROBE = 0, int KMODE = KM_ACC, bool TMA = false,
-          bool HALF = false>
+          bool HALF = false, bool PLAN = false>
 int launch_run(FwdParams p, cudaStream_t st) {
     constexpr int VE = VecTraits<TIn>::VE;
     constexpr int R = NW / KSPLIT;
@@ -42,7 +63,7 @@ int launch_run(FwdParams p, cudaStream_t st) {
     p.fsy16 = (int)(p.fs_y / VE);
     p.fsx16 = (int)(p.fs_x / VE);
     p.rcpV = 1.0f / (float)p.V;
-    auto kern = warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE, TMA, HALF>;
+    auto kern = warp_fuse_run_kernel<TIn, TOut, CELLS, NW, KSPLIT, MAXREG, DEPTH, CA, PROBE, KMODE, TMA, HALF, PLAN>;
     const size_t smem = (size_t)run_tables_bytes(p.V, CELLS, R) + (size_t)NW * DEPTH * 2048 + (size_t)p.V * 48 + (size_t)NW * DEPTH * 8;  // tables, rings, homographies, ring barriers
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return set_error(BEVIPM_ERR_CUDA, cudaGetErrorString(cudaGetLastError()));
