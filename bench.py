@@ -155,12 +155,16 @@ def measure_traffic_live(workload: str, variant: int, requested_variant: int = 0
     try:
         out = subprocess.run(cmd, capture_output=True, text=True, timeout=600).stdout
         rows = [r for r in csv.reader(io.StringIO(out)) if len(r) > 5]
+        while rows and "Metric Name" not in rows[0]:   # (the child's own JSON line and ==PROF== chatter share the stream)
+            rows.pop(0)
+        if not rows:
+            return None, "ncu printed no metric table"
         hdr = rows[0]
         mi, vi, ui = hdr.index("Metric Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
         scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
         tot = 0.0
         for r in rows[1:]:
-            if r[mi].startswith("dram__bytes_"):
+            if len(r) > max(mi, vi, ui) and r[mi].startswith("dram__bytes_"):
                 tot += float(r[vi].replace(",", "")) * scale.get(r[ui], 1)
         if tot <= 0:
             return None, "ncu returned no dram__bytes rows"
