@@ -8,6 +8,11 @@ zeros, align_corners=False) at 2*loc-1, times the attention weights, summed over
 MVDeTr applies with one level per camera view.  Two independent forms are kept so they can check each
 other: the grid_sample form and a scalar numpy form of the CUDA reference kernel's formula
 (h_im = loc_y*H - 0.5, per-tap bounds, w1*v1 + w2*v2 + w3*v3 + w4*v4, times the weight).
+
+PINNED TO A PUBLISHED THIRD-PARTY IMPLEMENTATION instead: tests/golden/deform_attn_hf.npz holds inputs, outputs and autograd
+gradients of `transformers` 5.5.0's `multi_scale_deformable_attention` (models/mask2former/modeling_mask2former.py, the
+PyTorch port of the algorithm above), produced by tests/golden/make_deform_golden.py from the unmodified installed package;
+tests/test_deform_attn.py::test_oracle_is_pinned_to_the_published_implementation checks both forms against it.
 """
 from __future__ import annotations
 
