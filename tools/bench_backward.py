@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""Time forward and backward (grad w.r.t. the features) of the fused op on a BASELINE shape, CUDA events.
+"""Time forward and backward (grad w.r.t. the features) of the fused op on a BASELINE shape, CUDA events, and beside it the
+reference's own op chain on ATen's CUDA kernels (oracle/torch_chain.py: one grid_sample per view + the view reduction, whose
+backward is ATen's grid_sampler_2d_backward + index_put / sum backward) on the same GPU and the same inputs.
 usage: bench_backward.py <workload> [mode]"""
 import sys
 from pathlib import Path
@@ -49,3 +51,30 @@ def fwd_bwd():
 tf = t(fwd)
 tb = t(fwd_bwd)
 print(f"{wl.name} B={B} mode={mode}: forward {tf:.3f} ms, forward+backward {tb:.3f} ms (backward incl. zero-fill of the gradient ~ {tb - tf:.3f} ms)")
+
+# the stock-torch arm: same chain as geometry.py:142-162 + fusion.py:17-22, autograd through ATen
+from oracle import torch_chain as tc  # noqa: E402  (development tool: the checker's restatement, never the product path)
+f2 = f.detach().float().contiguous().requires_grad_(True)          # NCHW-contiguous, what grid_sample wants
+K4 = Kd
+R4 = torch.cat([Rd, torch.tensor([0.0, 0.0, 0.0, 1.0], device=dev).expand(B, V, 1, 4)], dim=2)
+
+
+def aten_fwd():
+    return tc.fuse(tc.warp_views(f2, K4, R4, xd, yd, wl.img_size), mode if mode != "none" else "concat")
+
+
+def aten_fwd_bwd():
+    f2.grad = None
+    o = aten_fwd()
+    o.backward(cot.reshape(o.shape) if cot.numel() == o.numel() else torch.ones_like(o))
+
+
+with torch.no_grad():
+    af = t(aten_fwd, 3)
+ab = t(aten_fwd_bwd, 3)
+g_ours = torch.autograd.grad(fwd(), f, cot)[0]
+o2 = aten_fwd()
+g_aten = torch.autograd.grad(o2, f2, cot.reshape(o2.shape))[0]
+rel = float((g_ours - g_aten).abs().max() / g_aten.abs().max())
+print(f"{wl.name} B={B} mode={mode}: ATen chain forward {af:.3f} ms, forward+backward {ab:.3f} ms (backward ~ {ab - af:.3f} ms); "
+      f"ours vs ATen backward: {(ab - af) / max(tb - tf, 1e-9):.1f}x faster, gradients differ by {rel:.2e} (max-normalised)")
