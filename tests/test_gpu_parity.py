@@ -589,9 +589,10 @@ def test_host_buffer_entry_never_reads_unsampled_staging_memory(monkeypatch):
 
 
 def test_host_buffer_entry_uploads_only_sampled_texels():
-    """The host entry copies, per frame, view and band of source rows, only the span of texels some BEV cell samples.
-    Every texel NO cell samples is poisoned with NaN in the HOST buffer: the result must still be the oracle's on the
-    clean features, and the bytes copied must lie between the sampled texels and the sampled rows."""
+    """The host entry uploads only texels some BEV cell samples: from pinned memory exactly those (a per-row bitmap drives the
+    gather kernel), from pageable memory the row spans that hold them.  Every texel NO cell samples is poisoned with NaN in
+    the HOST buffer: the result must still be the oracle's on the clean features, and the bytes copied must be exactly the
+    sampled texels (pinned) / lie between them and the sampled rows (pageable)."""
     from bevipm import _lib, ops
     B, V, C, fhw, bhw = 2, 5, 32, (40, 64), (24, 72)
     feats, K, Rt, xs, ys, img = _rig_case(B, V, C, fhw, bhw, seed=17)
@@ -616,6 +617,12 @@ def test_host_buffer_entry_uploads_only_sampled_texels():
                              torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
     assert _same(out.numpy().transpose(0, 3, 1, 2), want)
     calib_bytes = (B * V * 21 + bhw[0] + bhw[1]) * 4
+    copied = int(_lib.load().bevipm_host_last_h2d_bytes()) - calib_bytes
+    assert copied == B * touched * C * 4
+    pageable = torch.from_numpy(nhwc.copy())
+    out = ops.warp_fuse_host(pageable, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                             torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+    assert _same(out.numpy().transpose(0, 3, 1, 2), want)
     copied = int(_lib.load().bevipm_host_last_h2d_bytes()) - calib_bytes
     assert B * touched * C * 4 <= copied <= B * row_texels * C * 4
 

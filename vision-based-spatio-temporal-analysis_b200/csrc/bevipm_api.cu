@@ -637,6 +637,9 @@ struct HostArena {
     float* calib = nullptr;
     int* rows = nullptr;        // device: touched x-span per (frame, view, source row)
     int* rows_host = nullptr;   // pinned host copy
+    unsigned* bits = nullptr;       // per (frame, view, source row): bitmap of the texels some BEV cell samples (device)
+    unsigned* bits_host = nullptr;  // pinned host copy (byte accounting)
+    size_t bits_words = 0;
     size_t rows_count = 0;
     uint64_t span_key = 0;      // hash of the calibration + shapes the cached span table belongs to (0 = none)
     size_t feat_bytes = 0, out_bytes = 0, calib_bytes = 0;
@@ -655,6 +658,9 @@ struct HostArena {
         if (calib) cudaFree(calib);
         if (rows) cudaFree(rows);
         if (rows_host) cudaFreeHost(rows_host);
+        if (bits) cudaFree(bits);
+        if (bits_host) cudaFreeHost(bits_host);
+        bits = nullptr; bits_host = nullptr; bits_words = 0;
         if (calib_ready) cudaEventDestroy(calib_ready);
         calib = nullptr; calib_ready = nullptr; rows = nullptr; rows_host = nullptr; rows_count = 0; span_key = 0;
         feat_bytes = out_bytes = calib_bytes = 0; device = -1;
@@ -692,7 +698,8 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
     CUDA_TRY(cudaGetDevice(&dev));
     HostArena& A = g_arena;
     const size_t nbv = (size_t)d.B * d.V * d.Hf;  // one x-span per (frame, view, source row)
-    if (A.device != dev || A.feat_bytes < fbytes || A.out_bytes < obytes || A.calib_bytes < cal_floats * 4 || A.rows_count < nbv) {
+    const int BW = (d.Wf + 31) / 32;   // bitmap words per source row
+    if (A.device != dev || A.feat_bytes < fbytes || A.out_bytes < obytes || A.calib_bytes < cal_floats * 4 || A.rows_count < nbv || A.bits_words < nbv * BW) {
         A.release();
         for (int s = 0; s < 2; ++s) {
             CUDA_TRY(cudaMalloc(&A.feats[s], fbytes));
@@ -705,12 +712,16 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
         CUDA_TRY(cudaMalloc(&A.calib, cal_floats * 4));
         CUDA_TRY(cudaMalloc(&A.rows, nbv * 2 * sizeof(int)));
         CUDA_TRY(cudaMallocHost(&A.rows_host, nbv * 2 * sizeof(int)));
+        CUDA_TRY(cudaMalloc(&A.bits, nbv * BW * sizeof(unsigned)));
+        CUDA_TRY(cudaMallocHost(&A.bits_host, nbv * BW * sizeof(unsigned)));
+        A.bits_words = nbv * BW;
         CUDA_TRY(cudaEventCreateWithFlags(&A.calib_ready, cudaEventDisableTiming));
         A.feat_bytes = fbytes; A.out_bytes = obytes; A.calib_bytes = cal_floats * 4; A.rows_count = nbv; A.device = dev;
     }
     // shape limits of the span kernel are checked before anything is queued
     if ((size_t)d.B * d.V > 65535) return fail(BEVIPM_ERR_UNSUPPORTED, "B*V too large");
-    if ((size_t)d.Hf * 8 > 40 * 1024) return fail(BEVIPM_ERR_UNSUPPORTED, "Hf=%d too tall for the span table of the host entry", d.Hf);
+    if ((size_t)d.Hf * (2 + (size_t)((d.Wf + 31) / 32)) * 4 > 40 * 1024)
+        return fail(BEVIPM_ERR_UNSUPPORTED, "Hf=%d x Wf=%d: too large for the span / bitmap table of the host entry", d.Hf, d.Wf);
     StreamQuiet quiet{A};
     float* dK = A.calib;
     float* dRt = dK + (size_t)d.B * d.V * 9;
@@ -742,10 +753,12 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
         CUDA_TRY(cudaMemcpyAsync(A.rows, A.rows_host, nbv * 2 * sizeof(int), cudaMemcpyHostToDevice, A.st[0]));
         FwdParams pr = make_params(&d, nullptr, dK, dRt, dxs, dys, nullptr);
         dim3 grid(ceil_div(d.Hb * d.Wb, 256), (unsigned)(d.B * d.V));
-        bevipm::touched_spans_kernel<<<grid, 256, (size_t)d.Hf * 2 * sizeof(int), A.st[0]>>>(pr, A.rows);
+        CUDA_TRY(cudaMemsetAsync(A.bits, 0, nbv * BW * sizeof(unsigned), A.st[0]));
+        bevipm::touched_spans_kernel<<<grid, 256, (size_t)d.Hf * (2 + BW) * sizeof(int), A.st[0]>>>(pr, A.rows, A.bits, BW);
         g_launches.fetch_add(1, std::memory_order_relaxed);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaMemcpyAsync(A.rows_host, A.rows, nbv * 2 * sizeof(int), cudaMemcpyDeviceToHost, A.st[0]));
+        CUDA_TRY(cudaMemcpyAsync(A.bits_host, A.bits, nbv * BW * sizeof(unsigned), cudaMemcpyDeviceToHost, A.st[0]));
     }
     CUDA_TRY(cudaEventRecord(A.calib_ready, A.st[0]));
     CUDA_TRY(cudaStreamWaitEvent(A.st[1], A.calib_ready, 0));
@@ -781,13 +794,14 @@ int bevipm_warp_fuse_host(const bevipm_desc* d_in, const void* feats, const floa
         const int s = f & 1;
         if (mapped && (gather_mode == 1 || (f & 1))) {
             const int texel16 = (int)(texel_bytes / 16);
-            dim3 grid(2, (unsigned)(d.V * d.Hf));
+            static const int gx = [] { const char* e = getenv("BEVIPM_GATHER_GX"); return e && atoi(e) > 0 ? atoi(e) : 2; }();  // CTAs per source row (development switch)
+            dim3 grid((unsigned)gx, (unsigned)(d.V * d.Hf));
             bevipm::host_span_gather_kernel<<<grid, 256, 0, A.st[s]>>>(mapped + (size_t)f * (fbytes / 16), static_cast<uint4*>(A.feats[s]),
-                                                                       A.rows + 2 * (size_t)f * d.V * d.Hf, d.Wf, texel16);
+                                                                       A.rows + 2 * (size_t)f * d.V * d.Hf, A.bits + (size_t)f * d.V * d.Hf * BW, BW, d.Wf, texel16);
             g_launches.fetch_add(1, std::memory_order_relaxed);
             CUDA_TRY(cudaGetLastError());
             for (size_t q = (size_t)f * d.V * d.Hf; q < (size_t)(f + 1) * d.V * d.Hf; ++q)
-                if (A.rows_host[2 * q] <= A.rows_host[2 * q + 1]) h2d += (int64_t)(A.rows_host[2 * q + 1] - A.rows_host[2 * q] + 1) * (int64_t)texel_bytes;
+                for (int w = 0; w < BW; ++w) h2d += (int64_t)__builtin_popcount(A.bits_host[q * BW + w]) * (int64_t)texel_bytes;
         } else
         for (int v = 0; v < d.V; ++v) {
             const int* sp = A.rows_host + 2 * ((size_t)f * d.V + v) * d.Hf;

@@ -162,15 +162,20 @@ __global__ void sample_coords_kernel(const FwdParams p, float* __restrict__ ix, 
 }
 
 // Source texels any BEV cell samples, per (frame, view) and source row: span[(bv * Hf + y) * 2] = first,
-// [.. + 1] = last x holding an in-map tap (first > last: nothing on that row).  Same projection and tap validity
-// as the fused kernels; the host-buffer entry uploads only these spans (rows above the horizon of a ground-plane
-// homography are never read).  span[] must be preset to {INT_MAX, -1}.
-__global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span) {
-    extern __shared__ int s_span[];  // [Hf][2]: this block's spans, flushed once (few rows per block are touched)
+// [.. + 1] = last x holding an in-map tap (first > last: nothing on that row), and -- when `bits` is given -- a bitmap of
+// exactly the texels that hold one (bits[(bv * Hf + y) * BW + x / 32] bit x % 32; far-field rows are sampled sparsely).
+// Same projection and tap validity as the fused kernels; the host-buffer entry uploads only these texels (rows above the
+// horizon of a ground-plane homography are never read).  span[] must be preset to {INT_MAX, -1}, bits[] to 0.
+// Dynamic shared memory: Hf * (2 + BW) ints.
+__global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span, unsigned* __restrict__ bits, int BW) {
+    extern __shared__ int s_span[];  // [Hf][2]: this block's spans, then [Hf][BW] its bitmap; flushed once (few rows per block are touched)
+    unsigned* s_bits = reinterpret_cast<unsigned*>(s_span + 2 * p.Hf);
     const int bv = blockIdx.y;
     __shared__ float H[9];
     if (threadIdx.x == 0) homography(p.K + 9 * bv, p.Rt + 12 * bv, H);
     for (int y = threadIdx.x; y < p.Hf; y += blockDim.x) { s_span[2 * y] = 0x7fffffff; s_span[2 * y + 1] = -1; }
+    if (bits)
+        for (int q = threadIdx.x; q < p.Hf * BW; q += blockDim.x) s_bits[q] = 0u;
     __syncthreads();
     const int cell = blockIdx.x * blockDim.x + threadIdx.x;
     if (cell < p.Hb * p.Wb) {
@@ -185,6 +190,7 @@ __global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span) 
             const int yy = t.y0 + (tap >> 1), xx = t.x0 + (tap & 1);
             atomicMin(s_span + 2 * yy, xx);
             atomicMax(s_span + 2 * yy + 1, xx);
+            if (bits) atomicOr(s_bits + yy * BW + (xx >> 5), 1u << (xx & 31));
         }
     }
     __syncthreads();
@@ -195,33 +201,41 @@ __global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span) 
             atomicMax(sv + 2 * y + 1, s_span[2 * y + 1]);
         }
     }
+    if (bits) {
+        unsigned* bvp = bits + (long long)bv * p.Hf * BW;
+        for (int q = threadIdx.x; q < p.Hf * BW; q += blockDim.x)
+            if (s_bits[q]) atomicOr(bvp + q, s_bits[q]);
+    }
 }
 
 // Host-buffer entry, upload side: the features lie in PINNED HOST memory that the device can address (UVA); this kernel
-// pulls exactly the texel spans some BEV cell samples (touched_spans_kernel's table: per view and source row [x_lo, x_hi])
-// over PCIe into the device arena, 16 bytes per lane and load, four loads in flight per thread.  One launch per frame
-// replaces ~60 banded cudaMemcpy2DAsync calls, moves no slack bytes (1.59 GB instead of 1.86 GB per config-1 step) and needs
-// no read-back of the table to the host.  blockIdx.y = (view, source row).
+// pulls exactly the texels some BEV cell samples (touched_spans_kernel's table: per view and source row [x_lo, x_hi] and the
+// bitmap of sampled texels inside it) over PCIe into the device arena.  A warp takes one sampled texel at a time, 16 bytes per
+// lane and load, up to four loads in flight per lane.  One launch per frame replaces ~60 banded cudaMemcpy2DAsync calls, moves no
+// slack bytes and needs no read-back of the table to the host.  blockIdx.y = (view, source row); gridDim.x CTAs share a row.
 __global__ void __launch_bounds__(256) host_span_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ spans,
-                                                                int Wf, int texel16) {
+                                                                const unsigned* __restrict__ bits, int BW, int Wf, int texel16) {
     const int row = blockIdx.y;
     const int lo = spans[2 * row], hi = spans[2 * row + 1];
     if (lo > hi) return;
-    const long long base = ((long long)row * Wf + lo) * texel16;
-    const long long n = (long long)(hi - lo + 1) * texel16;
-    const uint4* s = src + base;
-    uint4* d = dst + base;
-    const long long step = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * step < n; i += 4 * step) {
-        uint4 a0, a1, a2, a3;
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "l"(s + i));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(s + i + step));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a2.x), "=r"(a2.y), "=r"(a2.z), "=r"(a2.w) : "l"(s + i + 2 * step));
-        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a3.x), "=r"(a3.y), "=r"(a3.z), "=r"(a3.w) : "l"(s + i + 3 * step));
-        d[i] = a0; d[i + step] = a1; d[i + 2 * step] = a2; d[i + 3 * step] = a3;
+    const unsigned* rb = bits + (long long)row * BW;
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    for (int t = lo + blockIdx.x * wpc + (threadIdx.x >> 5); t <= hi; t += gridDim.x * wpc) {
+        if (!((rb[t >> 5] >> (t & 31)) & 1u)) continue;   // inside the span, but no cell samples it (warp-uniform)
+        const long long base = ((long long)row * Wf + t) * texel16;
+        const uint4* s = src + base;
+        uint4* d = dst + base;
+        int e = lane;
+        for (; e + 96 < texel16; e += 128) {
+            uint4 a0, a1, a2, a3;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a0.x), "=r"(a0.y), "=r"(a0.z), "=r"(a0.w) : "l"(s + e));
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a1.x), "=r"(a1.y), "=r"(a1.z), "=r"(a1.w) : "l"(s + e + 32));
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a2.x), "=r"(a2.y), "=r"(a2.z), "=r"(a2.w) : "l"(s + e + 64));
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(a3.x), "=r"(a3.y), "=r"(a3.z), "=r"(a3.w) : "l"(s + e + 96));
+            d[e] = a0; d[e + 32] = a1; d[e + 64] = a2; d[e + 96] = a3;
+        }
+        for (; e < texel16; e += 32) d[e] = __ldg(s + e);
     }
-    for (; i < n; i += step) d[i] = __ldg(s + i);
 }
 
 // fusion.py:17-22 on materialised maps: in [B,V,inner] -> out [B,inner]; sequential over v.
