@@ -230,7 +230,8 @@ int bevipm_warp_fuse_host(const bevipm_desc *d, const void *feats, const float *
 /* The staging arena (two frames of features + BEV on the device, two streams) is PER HOST THREAD and lives until that thread
  * calls bevipm_host_release(): a thread that stops using the entry must call it, nothing frees the arena at thread exit.
  * Pinned, device-addressable `feats` (cudaHostAlloc / torch pin_memory) are pulled over PCIe by a gather kernel that reads
- * exactly the sampled texels (a per-row bitmap, computed once per calibration); other host memory takes banded 2-D copies of the row spans.  On failure both streams are drained before the
+ * exactly the sampled texels (a per-row bitmap, computed once per calibration) while the copy engine uploads each view's run of
+ * densely sampled rows beside it; other host memory takes banded 2-D copies of the row spans.  On failure both streams are drained before the
  * call returns, so the caller's buffers are never in flight after it. */
 void bevipm_host_release(void);
 /* Host-to-device bytes the last bevipm_warp_fuse_host call of this thread copied: the entry uploads, per frame,

@@ -588,11 +588,12 @@ def test_host_buffer_entry_never_reads_unsampled_staging_memory(monkeypatch):
     monkeypatch.delenv("BEVIPM_HOST_POISON")
 
 
-def test_host_buffer_entry_uploads_only_sampled_texels():
-    """The host entry uploads only texels some BEV cell samples: from pinned memory exactly those (a per-row bitmap drives the
-    gather kernel), from pageable memory the row spans that hold them.  Every texel NO cell samples is poisoned with NaN in
-    the HOST buffer: the result must still be the oracle's on the clean features, and the bytes copied must be exactly the
-    sampled texels (pinned) / lie between them and the sampled rows (pageable)."""
+def test_host_buffer_entry_uploads_only_sampled_texels(monkeypatch):
+    """The host entry uploads only texels some BEV cell samples: from pinned memory exactly those when the gather kernel works
+    alone (a per-row bitmap drives it), those plus the holes of the dense rows the copy engine takes in the default mode, and
+    from pageable memory the row spans that hold them.  Every texel NO cell samples is poisoned with NaN in the HOST buffer:
+    the result must still be the oracle's on the clean features, and the bytes copied must be exactly the sampled texels
+    (gather alone) / lie between them and the sampled rows (default, pageable)."""
     from bevipm import _lib, ops
     B, V, C, fhw, bhw = 2, 5, 32, (40, 64), (24, 72)
     feats, K, Rt, xs, ys, img = _rig_case(B, V, C, fhw, bhw, seed=17)
@@ -613,12 +614,21 @@ def test_host_buffer_entry_uploads_only_sampled_texels():
         row_texels += int(hit.any(axis=1).sum()) * fhw[1]
     assert touched < row_texels < V * fhw[0] * fhw[1]
     host = torch.from_numpy(nhwc).pin_memory()
+    calib_bytes = (B * V * 21 + bhw[0] + bhw[1]) * 4
+    monkeypatch.setenv("BEVIPM_HOST_DMA_DENSE", "0")          # the gather kernel alone
     out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
                              torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
     assert _same(out.numpy().transpose(0, 3, 1, 2), want)
-    calib_bytes = (B * V * 21 + bhw[0] + bhw[1]) * 4
     copied = int(_lib.load().bevipm_host_last_h2d_bytes()) - calib_bytes
     assert copied == B * touched * C * 4
+    for dense in ("0.8", "0.3"):                              # default: dense rows through the copy engine; and a low threshold
+        monkeypatch.setenv("BEVIPM_HOST_DMA_DENSE", dense)
+        out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                                 torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")
+        assert _same(out.numpy().transpose(0, 3, 1, 2), want)
+        copied = int(_lib.load().bevipm_host_last_h2d_bytes()) - calib_bytes
+        assert B * touched * C * 4 <= copied <= B * row_texels * C * 4
+    monkeypatch.delenv("BEVIPM_HOST_DMA_DENSE")
     pageable = torch.from_numpy(nhwc.copy())
     out = ops.warp_fuse_host(pageable, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
                              torch.from_numpy(xs), torch.from_numpy(ys), img, "mean")

@@ -214,8 +214,13 @@ __global__ void touched_spans_kernel(const FwdParams p, int* __restrict__ span, 
 // lane and load, up to four loads in flight per lane.  One launch per frame replaces ~60 banded cudaMemcpy2DAsync calls, moves no
 // slack bytes and needs no read-back of the table to the host.  blockIdx.y = (view, source row); gridDim.x CTAs share a row.
 __global__ void __launch_bounds__(256) host_span_gather_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, const int* __restrict__ spans,
-                                                                const unsigned* __restrict__ bits, int BW, int Wf, int texel16) {
+                                                                const unsigned* __restrict__ bits, int BW, int Wf, int texel16,
+                                                                const int* __restrict__ dma_rows, int Hf) {
     const int row = blockIdx.y;
+    {   // rows the copy engine uploads (a run of dense rows per view; empty run: first > last)
+        const int v = row / Hf, y = row - v * Hf;
+        if (y >= dma_rows[2 * v] && y <= dma_rows[2 * v + 1]) return;
+    }
     const int lo = spans[2 * row], hi = spans[2 * row + 1];
     if (lo > hi) return;
     const unsigned* rb = bits + (long long)row * BW;
