@@ -758,7 +758,7 @@ def run_ours(args, wl):
         e2e = {"value": world * B * n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "host_feature_bytes_per_step": hf.numel() * hf.element_size(),
                "d2h_bytes_per_step": ho.numel() * ho.element_size(), "steps": n_e2e, "ms_per_step": dt / n_e2e * 1e3,
-               "api": "bevipm_warp_fuse_host (pinned host in -> H2D of the source-row spans any BEV cell samples -> fused kernel -> "
+               "api": "bevipm_warp_fuse_host (pinned host in -> H2D of exactly the texels some BEV cell samples (gather kernel over a per-row bitmap + the dense rows by the copy engine) -> fused kernel -> "
                       "D2H -> pinned host out, double-buffered per frame)", "matches_device_path": ok}
         e2e["numa"] = numa
         _lib.load().bevipm_host_release()
