@@ -569,6 +569,29 @@ def test_host_buffer_entry_matches_oracle(monkeypatch, pinned, gather):
     assert _same(out.numpy().transpose(0, 3, 1, 2), orc.warp_fuse(feats, K2, Rt2, xs, ys, img, "mean"))
 
 
+@pytest.mark.parametrize("dense", ["0", "0.8", "0.4"])
+def test_host_buffer_entry_with_per_frame_calibration_and_modes(monkeypatch, dense):
+    """Every frame has its own cameras (its own spans, bitmaps and copy-engine rows), an odd number of frames goes through the
+    two staging buffers, and the per-view output mode takes the same upload path: gather kernel alone and with the dense
+    rows of each view uploaded by the copy engine beside it."""
+    from bevipm import ops
+    monkeypatch.setenv("BEVIPM_HOST_DMA_DENSE", dense)
+    B, V, C, fhw, bhw = 5, 4, 64, (27, 48), (24, 72)
+    feats, K, Rt, xs, ys, img = _rig_case(B, V, C, fhw, bhw, seed=23)
+    K, Rt = K.copy(), Rt.copy()
+    for b in range(1, B):
+        Kb, Rb = _rig_case(1, V, C, fhw, bhw, seed=23 + b)[1:3]
+        K[b], Rt[b] = Kb[0], Rb[0]
+    host = torch.from_numpy(np.ascontiguousarray(feats.transpose(0, 1, 3, 4, 2))).pin_memory()
+    for mode in ("mean", "none"):
+        want = orc.warp_fuse(feats, K, Rt, xs, ys, img, mode)
+        for _ in range(2):
+            out = ops.warp_fuse_host(host, torch.from_numpy(K), torch.from_numpy(Rt[:, :, :3, :]).contiguous(),
+                                     torch.from_numpy(xs), torch.from_numpy(ys), img, mode).numpy()
+            got = out.transpose(0, 3, 1, 2) if mode == "mean" else out.transpose(0, 1, 4, 2, 3)
+            assert _same(got, want), (mode, dense)
+
+
 def test_host_buffer_entry_never_reads_unsampled_staging_memory(monkeypatch):
     """The device staging arena is only partially written (sampled spans): with the arena poisoned with NaN patterns
     (BEVIPM_HOST_POISON) the result must still be the oracle's -- no kernel reads a texel that was not uploaded."""
