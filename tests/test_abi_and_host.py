@@ -181,6 +181,37 @@ def test_round2_entry_points_check_their_arguments():
     assert L.bevipm_warp_fuse_red(ctypes.byref(d), dummy, ctypes.cast(dummy, ctypes.c_void_p), dummy, dummy, dummy, arr, 2, 2, None) == -2
 
 
+def test_projection_and_table_cache_entry_points_check_their_arguments():
+    """bevipm_proj1x1 / bevipm_plan_bytes / bevipm_warp_fuse_fwd_planned: every shape and pointer rule is checked on the host
+    before anything touches the device (so these run without a GPU)."""
+    from bevipm import _lib
+    L = _lib.load()
+    p16 = ctypes.c_void_p(1 << 20)
+    # null pointers / bad pass count / output-channel rule / 16-byte rules
+    assert L.bevipm_proj1x1(None, p16, None, p16, 7, 7, 100, 64, 128, 64, 6400, 128, 12800, 1, None) == -1
+    assert L.bevipm_proj1x1(p16, p16, None, p16, 7, 7, 100, 64, 128, 64, 6400, 128, 12800, 2, None) == -1
+    assert L.bevipm_proj1x1(p16, p16, None, p16, 7, 7, 100, 64, 128, 64, 6400, 128, 12800, 3, None) == -1      # split mode without w_lo
+    assert L.bevipm_proj1x1(p16, p16, None, p16, 7, 7, 100, 64, 24, 64, 6400, 24, 2400, 1, None) == -2          # Co not a multiple of 16
+    assert L.bevipm_proj1x1(p16, p16, None, p16, 7, 7, 100, 64, 272, 64, 6400, 272, 27200, 1, None) == -2       # Co > 256
+    assert L.bevipm_proj1x1(p16, p16, None, p16, 7, 7, 100, 30, 128, 30, 3000, 128, 12800, 1, None) == -2       # C not a multiple of 4
+    assert L.bevipm_proj1x1(ctypes.c_void_p((1 << 20) + 4), p16, None, p16, 7, 7, 100, 64, 128, 64, 6400, 128, 12800, 1, None) == -1
+    assert b"proj1x1" in L.bevipm_last_error()
+    d = _lib.Desc()
+    d.B, d.V, d.C, d.Hf, d.Wf, d.Hb, d.Wb, d.img_h, d.img_w = 1, 7, 128, 27, 48, 120, 360, 1080, 1920
+    d.mode = _lib.MEAN
+    per_segment = 7 * 8 * 16 + (7 * 8 + 8) * 16 + ((7 * 20 + 12 + 15) // 16) * 16      # weights, load list, masks (csrc/ipm_run.cuh)
+    assert L.bevipm_plan_bytes(ctypes.byref(d)) == 4096 + 45 * 120 * per_segment
+    d.Hb = 121                                                                            # rows are padded to the CTA's four
+    assert L.bevipm_plan_bytes(ctypes.byref(d)) == 4096 + 45 * 124 * per_segment
+    d.V = 33
+    assert L.bevipm_plan_bytes(ctypes.byref(d)) == -1
+    d.V, d.Hb = 7, 120
+    assert L.bevipm_warp_fuse_fwd_planned(ctypes.byref(d), p16, p16, p16, p16, p16, p16, None, 0, None) == -1  # no cache buffer
+    assert L.bevipm_warp_fuse_fwd_planned(ctypes.byref(d), p16, p16, p16, p16, p16, p16, p16, 1024, None) == -1  # too small
+    d.variant = 21
+    assert L.bevipm_warp_fuse_fwd_planned(ctypes.byref(d), p16, p16, p16, p16, p16, p16, p16, 1 << 30, None) == -1  # default kernels only
+
+
 def test_kornia_decision_mirrors_the_reference():
     """geometry.py:5-9 + :124: the kornia branch runs iff warp_impl == 'kornia' AND kornia imports.  kornia is not installed
     in this image, so warp_impl='kornia' (what BEVNet passes, model_wrapper.py:42) resolves to the grid_sample geometry."""
